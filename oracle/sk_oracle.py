@@ -1,0 +1,79 @@
+"""CPU oracle (numpy, float64) of the reference Sinkhorn-Knopp solver.  TEST INFRASTRUCTURE ONLY.
+
+Restates /root/reference/src/sk_utils.py:359-422 (`optimize_L_sk_gpu`) line by line; the random draw of
+the Gaussian marginals (sk_utils.py:372,377) is an INPUT here (`kdist`) so that the oracle, the reference
+and the CUDA kernel can share it.  Pinned against the reference itself (device strings substituted, see
+oracle/ref_loader.py) by tests/golden/gen_golden.py -> tests/golden/sk_*.npz, checked in
+tests/test_oracle.py.
+"""
+import numpy as np
+
+
+def sk_marginals(PS, kdist):
+    """sk_utils.py:369,388-392: scatter the target sizes by the argsort of the current cluster masses.
+
+    NOTE the reference quirk: `_K_dist` is [K,1] and `torch.sort(_K_dist)` sorts along the LAST dimension
+    (size 1), i.e. it is the identity; line 388 therefore computes  new[argsort[i]] = old[i]  (a permutation
+    scatter, no sorting).  Verified against the reference itself (tests/golden/sk_cases.npz, kdist_after).
+
+    PS [N,K] f64 (un-powered), kdist [K] f64 or None ('default' distribution: ones).
+    Returns (r [K], kdist_permuted [K])."""
+    K = PS.shape[1]
+    if kdist is None:
+        kd = np.ones(K, dtype=np.float64)
+    else:
+        kd = np.array(kdist, dtype=np.float64).reshape(K).copy()
+        order = np.argsort(PS.sum(0), kind="stable")      # marginals_argsort (:369)
+        kd[order] = kd.copy()                             # _K_dist[marginals_argsort] = sort(_K_dist, dim=-1)[0] (:388)
+    r = 1.0 / kd                                          # (:392)
+    r = r / r.sum()                                       # (:393)
+    return r, kd
+
+
+def optimize_L_sk(PS, lamb=20.0, kdist=None, max_iters=2000, check_every=10, tol=1e-1,
+                  stop_on_converge=True):
+    """Returns dict(cost, labels, alpha, beta, iters, err, kdist).  PS is not modified."""
+    PS = np.array(PS, dtype=np.float64)
+    N, K = PS.shape
+    r, kd = sk_marginals(PS, kdist)
+    beta = np.full(N, 1.0 / N)                            # (:390)
+    PS = PS ** (0.5 * lamb)                               # (:391)
+    c = 1.0 / N                                           # (:395)
+    err = 1e6
+    it = 0
+    alpha = None
+    while ((err > tol) if stop_on_converge else True) and it < max_iters:   # (:400)
+        alpha = r / (beta @ PS)                           # (:401)
+        beta_new = c / (PS @ alpha)                       # (:402)
+        if it % check_every == 0:                         # (:403)
+            err = float(np.sum(np.abs(beta / beta_new - 1.0)))
+        beta = beta_new
+        it += 1
+    P = (PS * beta[:, None]) * alpha[None, :]             # (:411-412)
+    labels = np.argmax(P, axis=1).astype(np.int64)        # (:413)
+    P = ((1.0 / alpha)[None, :] * P) * (1.0 / beta)[:, None]   # (:416-417)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sol = np.nansum(np.log(P[np.arange(N), labels]))  # (:418)
+    cost = -(1.0 / lamb) * sol / N                        # (:419)
+    return dict(cost=float(cost), labels=labels, alpha=alpha, beta=beta, iters=it, err=err, kdist=kd)
+
+
+def top2_margin(PS, lamb, alpha, beta):
+    """Relative gap between the best and second-best entry of each row of the scaled matrix — used by the
+    parity tests to tell a genuine mismatch from an ulp-level tie."""
+    P = (np.array(PS, dtype=np.float64) ** (0.5 * lamb)) * beta[:, None] * alpha[None, :]
+    part = np.partition(P, -2, axis=1)
+    best, second = part[:, -1], part[:, -2]
+    return (best - second) / np.maximum(best, 1e-300)
+
+
+def synth_PS(N, K, scale=1.0, seed=0):
+    """cfg-5 style input: softmax(randn*s) * softmax(randn*s), float64, numpy RNG."""
+    rng = np.random.default_rng(seed)
+
+    def sm(x):
+        x = x - x.max(1, keepdims=True)
+        e = np.exp(x)
+        return e / e.sum(1, keepdims=True)
+
+    return sm(rng.standard_normal((N, K)) * scale) * sm(rng.standard_normal((N, K)) * scale)

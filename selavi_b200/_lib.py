@@ -1,0 +1,82 @@
+"""ctypes binding of libselavi_b200.so (the C ABI declared in include/selavi_b200.h).
+
+The product path has NO CPU fallback: if the shared library is missing or a call fails, this module
+raises.  PyTorch is only used by callers for device memory, streams and torch.distributed.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libselavi_b200.so")
+
+_lib = None
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_ll = ctypes.c_longlong
+c_double = ctypes.c_double
+c_float = ctypes.c_float
+c_size_t = ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/selavi_b200.h (tests check this)
+SIGNATURES = {
+    "selavi_version": (c_int, []),
+    "selavi_last_error": (ctypes.c_char_p, []),
+    "selavi_sk_workspace_bytes": (c_size_t, [c_int]),
+    "selavi_sk_kp": (c_int, [c_int]),
+    "selavi_sk_solve": (c_int, [c_void_p, c_ll, c_ll, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_int, c_int, c_double, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "selavi_conv_tiles": (c_int, [c_int, c_void_p, c_void_p]),
+    "selavi_conv_wpack_bytes": (c_size_t, [c_int, c_int]),
+    "selavi_conv_pack_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "selavi_conv_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                 c_int, c_void_p]),
+    "selavi_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_ll]),
+    "selavi_conv_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                  c_int, c_int, c_void_p]),
+    "selavi_symm_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
+    "selavi_symm_open": (c_int, [c_void_p, c_void_p]),
+    "selavi_symm_close": (c_int, [c_void_p]),
+    "selavi_symm_free": (c_int, [c_void_p]),
+    "selavi_symm_memset": (c_int, [c_void_p, c_int, c_size_t, c_void_p]),
+}
+
+
+class SelaviError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the CUDA extension is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SelaviError(
+                f"{LIB_PATH} not found: build it with `python -m selavi_b200.build` "
+                "(no CPU fallback exists for the selavi_b200 hot path)")
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = lib().selavi_last_error()
+        raise SelaviError(f"{what} failed with code {code}: {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

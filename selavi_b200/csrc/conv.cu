@@ -1,0 +1,490 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 / TMEM), forward and data-gradient.
+//
+// Replaces the cuDNN calls behind torchvision's Conv2Plus1D / BasicBlock / stem / downsample convolutions
+// (tv:video/resnet.py:45-61,184-195,276-281; tv:resnet.py:59-105) that the reference model is made of
+// (model.py:93-121).  Activations are channels-last fp32 ([N,T,H,W,Cs], Cs = channels padded to 4).
+//
+//   dst[m, n] = sum_{tap, c} P(src)[pix(m, tap), c] * W[n, tap, c]        m = output pixel, n = output channel
+//
+// One CTA computes a 128-pixel x BNt-channel tile (BNt <= 256, fp32 accumulator in TMEM).
+//   * A operand (pixels x K): gathered by 8 loader warps with 16-byte loads (im2col on the fly, zero padding,
+//     stride, or the transposed gather of the data gradient), passed through an optional fused prologue
+//     P(x) = relu(x*scale[c] + shift[c])  — the train-mode BatchNorm+ReLU of the PREVIOUS layer, so normalised
+//     activations are never written to HBM — split into tf32 hi/lo words and stored into 128B-swizzled
+//     K-major tiles in shared memory.
+//   * B operand (weights): pre-tiled, pre-swizzled and pre-split on the device once per optimizer step
+//     (conv_pack_weights), fetched with one 1-D TMA bulk copy per stage.
+//   * MMA: one thread issues tcgen05.mma.kind::tf32; `passes`=3 computes hi*hi + hi*lo + lo*hi (fp32-class
+//     accuracy, error ~2^-21; needed because train-mode BN amplifies operand rounding ~80x),
+//     `passes`=1 is plain tf32.
+//   * Epilogue: TMEM -> registers -> global (float4), plus per-tile per-channel sum / sum-of-squares partials
+//     for the following BatchNorm (deterministic two-stage reduction, no atomics).
+#include <stdint.h>
+
+#include "../../include/selavi_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int BM = 128;            // pixels per tile (UMMA M)
+constexpr int BK = 32;             // fp32 elements per K stage (one 128B swizzle row)
+constexpr int LOADER_WARPS = 8;
+constexpr int LOADER_THREADS = LOADER_WARPS * 32;
+constexpr int MMA_WARP = LOADER_WARPS;
+constexpr int BPROD_WARP = LOADER_WARPS + 1;
+constexpr int CONV_THREADS = (LOADER_WARPS + 2) * 32;
+constexpr int A_TILE_BYTES = BM * 128;
+constexpr int MAX_TAPS = 64;
+
+struct ConvParams {
+    const float* src;
+    float* dst;
+    const unsigned char* wpack;  // [ntiles][kstages][2][BNt][128B]
+    const float* pro_scale;      // [cs] or null
+    const float* pro_shift;
+    float* stats;                // [m_tiles][2][ntiles*BNt] or null
+    int mode;                    // 0 fwd, 1 dgrad
+    int nb, ts, hs, ws, cs;      // src geometry
+    int td, hd, wd, cd;          // dst geometry
+    int kt, kh, kw, st, sh, sw, pt, ph, pw;
+    int M;                       // nb*td*hd*wd
+    int kchunks;                 // taps * cs/4   (16-byte chunks along K)
+    int kstages;                 // ceil(kchunks / 8)
+    int bnt, ntiles, stages;
+    int pro_relu, accumulate, passes;
+    uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // carve: [stages x (A_hi | A_lo | B_hi | B_lo)] [barriers] [tap table] [stat scratch]
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_tile_bytes = p.bnt * 128;
+    const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
+    unsigned char* tail = smem + (size_t)p.stages * stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);       // [stages]
+    uint64_t* empty_bar = full_bar + 8;                            // [stages]
+    uint64_t* accum_bar = empty_bar + 8;                           // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    int* tap_dt = reinterpret_cast<int*>(tmem_slot + 2);           // [MAX_TAPS] packed (kt | kh<<8 | kw<<16)
+    float* s_stat = reinterpret_cast<float*>(tap_dt + MAX_TAPS);   // [LOADER_WARPS][2][16] per 16-col unit
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * BM;
+    const int ntile = blockIdx.y;
+    const int taps = p.kt * p.kh * p.kw;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            sv::mbar_init(&full_bar[s], LOADER_WARPS + 1);
+            sv::mbar_init(&empty_bar[s], 1);
+        }
+        sv::mbar_init(accum_bar, 1);
+        sv::fence_barrier_init();
+    }
+    for (int t = tid; t < taps; t += CONV_THREADS) {
+        const int kw_ = t % p.kw, kh_ = (t / p.kw) % p.kh, kt_ = t / (p.kw * p.kh);
+        tap_dt[t] = kt_ | (kh_ << 8) | (kw_ << 16);
+    }
+    if (warp == MMA_WARP) {
+        sv::tmem_alloc(tmem_slot, p.tmem_cols);
+        sv::tmem_relinquish();
+    }
+    sv::tc_fence_before();
+    __syncthreads();
+    sv::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < LOADER_WARPS) {
+        // ------------------------------------------------------------------ A loaders
+        const int c = tid & 7;    // 16-byte chunk within the 128B K row
+        const int r0 = tid >> 3;  // rows r0 + 32*j
+        const int C4 = p.cs >> 2;
+        int pixn[4];              // n * (ts*hs*ws) or -1 when the row is past M
+        int dcoord[4];            // packed dst coords t | h<<10 | w<<21
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = m0 + r0 + 32 * j;
+            if (m < p.M) {
+                int w_ = m % p.wd;
+                int t1 = m / p.wd;
+                int h_ = t1 % p.hd;
+                int t2 = t1 / p.hd;
+                int t_ = t2 % p.td;
+                int n_ = t2 / p.td;
+                pixn[j] = n_ * (p.ts * p.hs * p.ws);
+                dcoord[j] = t_ | (h_ << 10) | (w_ << 21);
+            } else {
+                pixn[j] = -1;
+                dcoord[j] = 0;
+            }
+        }
+        int tap = 0, c4 = c;  // flattened K chunk q = 8*ks + c  ->  (tap, c4)
+        while (c4 >= C4) {
+            c4 -= C4;
+            ++tap;
+        }
+        const uint32_t sw_off = (uint32_t)((c ^ (r0 & 7)) << 4);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int ks = 0; ks < p.kstages; ++ks) {
+            // issue the gathers first (they do not depend on the smem slot), then wait for the slot
+            float4 v[4];
+            bool okv[4];
+            const bool kvalid = tap < taps;
+            int kt_ = 0, kh_ = 0, kw_ = 0;
+            if (kvalid) {
+                const int pk = tap_dt[tap];
+                kt_ = pk & 255;
+                kh_ = (pk >> 8) & 255;
+                kw_ = (pk >> 16) & 255;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                bool ok = kvalid && pixn[j] >= 0;
+                int t_ = dcoord[j] & 1023, h_ = (dcoord[j] >> 10) & 2047, w_ = (dcoord[j] >> 21) & 1023;
+                int a, b, d;
+                if (p.mode == 0) {
+                    a = t_ * p.st - p.pt + kt_;
+                    b = h_ * p.sh - p.ph + kh_;
+                    d = w_ * p.sw - p.pw + kw_;
+                } else {
+                    a = t_ + p.pt - kt_;
+                    b = h_ + p.ph - kh_;
+                    d = w_ + p.pw - kw_;
+                    if (p.st == 2) { ok &= !(a & 1); a >>= 1; }
+                    if (p.sh == 2) { ok &= !(b & 1); b >>= 1; }
+                    if (p.sw == 2) { ok &= !(d & 1); d >>= 1; }
+                }
+                ok &= (a >= 0) & (a < p.ts) & (b >= 0) & (b < p.hs) & (d >= 0) & (d < p.ws);
+                if (ok) {
+                    const size_t pix = (size_t)(pixn[j] + (a * p.hs + b) * p.ws + d);
+                    v[j] = __ldg(reinterpret_cast<const float4*>(p.src + pix * p.cs + c4 * 4));
+                }
+                okv[j] = ok;
+            }
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sf = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.pro_scale != nullptr && kvalid) {
+                sc = __ldg(reinterpret_cast<const float4*>(p.pro_scale + c4 * 4));
+                sf = __ldg(reinterpret_cast<const float4*>(p.pro_shift + c4 * 4));
+            }
+            sv::mbar_wait(&empty_bar[stage], phase ^ 1);
+            const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 x = v[j];
+                if (p.pro_scale != nullptr && okv[j]) {
+                    x.x = fmaf(x.x, sc.x, sf.x);
+                    x.y = fmaf(x.y, sc.y, sf.y);
+                    x.z = fmaf(x.z, sc.z, sf.z);
+                    x.w = fmaf(x.w, sc.w, sf.w);
+                    if (p.pro_relu) {
+                        x.x = fmaxf(x.x, 0.f);
+                        x.y = fmaxf(x.y, 0.f);
+                        x.z = fmaxf(x.z, 0.f);
+                        x.w = fmaxf(x.w, 0.f);
+                    }
+                }
+                const uint32_t row_off = (uint32_t)((r0 + 32 * j) * 128) + sw_off;
+                const uint32_t h0 = tf32_hi(x.x), h1 = tf32_hi(x.y), h2 = tf32_hi(x.z), h3 = tf32_hi(x.w);
+                st_shared_v4(a_hi + row_off, h0, h1, h2, h3);
+                if (p.passes == 3) {
+                    st_shared_v4(a_lo + row_off, __float_as_uint(x.x - __uint_as_float(h0)),
+                                 __float_as_uint(x.y - __uint_as_float(h1)), __float_as_uint(x.z - __uint_as_float(h2)),
+                                 __float_as_uint(x.w - __uint_as_float(h3)));
+                }
+            }
+            sv::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) sv::mbar_arrive(&full_bar[stage]);
+            // advance K position by 8 chunks
+            c4 += 8;
+            while (c4 >= C4 && tap < taps) {
+                c4 -= C4;
+                ++tap;
+            }
+            if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+
+        // ------------------------------------------------------------------ epilogue (same 8 warps)
+        sv::mbar_wait(accum_bar, 0);
+        sv::tc_fence_after();
+        const int quad = warp & 3, half = warp >> 2;
+        const int units = p.bnt >> 4;                   // 16-column units
+        const int u_begin = half == 0 ? 0 : (units + 1) / 2;
+        const int u_end = half == 0 ? (units + 1) / 2 : units;
+        const int m = m0 + quad * 32 + lane;
+        const bool row_ok = m < p.M;
+        const int n_base = ntile * p.bnt;
+        float* out_row = p.dst + (size_t)(row_ok ? m : 0) * p.cd;
+        for (int u = u_begin; u < u_end; ++u) {
+            uint32_t acc[16];
+            sv::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(u * 16), acc);
+            sv::tmem_ld_wait();
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(acc[i]);
+            const int ncol = n_base + u * 16;
+            if (row_ok) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    if (ncol + i < p.cd) {
+                        float4* dp = reinterpret_cast<float4*>(out_row + ncol + i);
+                        float4 o = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                        if (p.accumulate) {
+                            const float4 old = *dp;
+                            o.x += old.x;
+                            o.y += old.y;
+                            o.z += old.z;
+                            o.w += old.w;
+                        }
+                        *dp = o;
+                    }
+                }
+            }
+            if (p.stats != nullptr) {
+                // column sums over this warp's 32 rows (rows past M hold exact zeros): transpose-reduce
+                float s1[16], s2[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    s1[i] = f[i];
+                    s2[i] = f[i] * f[i];
+                }
+#pragma unroll
+                for (int off = 16, n = 8; off >= 2; off >>= 1, n >>= 1) {
+                    const bool upper = (lane & off) != 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (i < n) {
+                            const float send1 = upper ? s1[i] : s1[i + n];
+                            const float keep1 = upper ? s1[i + n] : s1[i];
+                            s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+                            const float send2 = upper ? s2[i] : s2[i + n];
+                            const float keep2 = upper ? s2[i + n] : s2[i];
+                            s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+                        }
+                    }
+                }
+                s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
+                s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
+                // lane L holds column (L >> 1) of this unit
+                float* sq = s_stat + (size_t)(warp * 2) * 16;
+                if ((lane & 1) == 0) {
+                    sq[lane >> 1] = s1[0];
+                    sq[16 + (lane >> 1)] = s2[0];
+                }
+                // the 4 quadrant warps of this column half combine (named barrier per half: 128 threads)
+                named_bar_sync(1 + half, 128);
+                if (quad == 0 && lane < 32) {
+                    const int which = lane >> 4, col = lane & 15;
+                    float tsum = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tsum += s_stat[(size_t)((half * 4 + q) * 2 + which) * 16 + col];
+                    const int ctot = p.ntiles * p.bnt;
+                    p.stats[((size_t)blockIdx.x * 2 + which) * ctot + ncol + col] = tsum;
+                }
+                named_bar_sync(1 + half, 128);
+            }
+        }
+        sv::tc_fence_before();
+    } else if (warp == MMA_WARP) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idesc = sv::make_idesc_tf32(BM, p.bnt, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ks = 0; ks < p.kstages; ++ks) {
+                sv::mbar_wait(&full_bar[stage], phase);
+                sv::tc_fence_after();
+                const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t a_lo = a_hi + A_TILE_BYTES;
+                const uint32_t b_hi = a_lo + A_TILE_BYTES;
+                const uint32_t b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const uint64_t da_hi = sv::make_smem_desc_sw128(a_hi + k4 * 32, 16, 1024);
+                    const uint64_t db_hi = sv::make_smem_desc_sw128(b_hi + k4 * 32, 16, 1024);
+                    if (p.passes == 3) {
+                        const uint64_t da_lo = sv::make_smem_desc_sw128(a_lo + k4 * 32, 16, 1024);
+                        const uint64_t db_lo = sv::make_smem_desc_sw128(b_lo + k4 * 32, 16, 1024);
+                        sv::umma_tf32(tmem_base, da_lo, db_hi, idesc, (ks | k4) ? 1u : 0u);
+                        sv::umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
+                        sv::umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
+                    } else {
+                        sv::umma_tf32(tmem_base, da_hi, db_hi, idesc, (ks | k4) ? 1u : 0u);
+                    }
+                }
+                sv::umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            sv::umma_commit(accum_bar);  // accumulator complete
+        }
+    } else {
+        // ------------------------------------------------------------------ B producer (one thread, TMA bulk)
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(p.passes == 3 ? 2 * b_tile_bytes : b_tile_bytes);
+            const unsigned char* wsrc = p.wpack + (size_t)ntile * p.kstages * 2 * b_tile_bytes;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ks = 0; ks < p.kstages; ++ks) {
+                sv::mbar_wait(&empty_bar[stage], phase ^ 1);
+                sv::mbar_arrive_expect_tx(&full_bar[stage], bytes);
+                sv::bulk_g2s(smem + (size_t)stage * stage_bytes + 2 * A_TILE_BYTES, wsrc + (size_t)ks * 2 * b_tile_bytes,
+                             bytes, &full_bar[stage]);
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        sv::tc_fence_after();
+        sv::tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// W (torch layout [co][ci][taps]) -> pre-tiled, pre-swizzled, hi/lo split B operand.
+//   mode 0 (fwd):   n = co, k = tap*cs + ci   (cs = padded ci)
+//   mode 1 (dgrad): n = ci, k = tap*cs + co   (cs = padded co)
+__global__ void conv_pack_weights_kernel(const float* __restrict__ W, int mode, int co, int ci, int taps, int cs,
+                                         int bnt, int ntiles, int kstages, float* __restrict__ out) {
+    const size_t total = (size_t)ntiles * kstages * bnt * 32;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(idx & 3);
+        const int c = (int)((idx >> 2) & 7);
+        const int n = (int)((idx >> 5) % bnt);
+        const size_t blk = (idx >> 5) / bnt;  // ntile*kstages + ks
+        const int ks = (int)(blk % kstages);
+        const int nt = (int)(blk / kstages);
+        const int k = ks * 32 + c * 4 + e;
+        const int tap = k / cs, kc = k % cs;
+        const int nn = nt * bnt + n;
+        float val = 0.f;
+        if (tap < taps) {
+            if (mode == 0) {
+                if (nn < co && kc < ci) val = W[((size_t)nn * ci + kc) * taps + tap];
+            } else {
+                if (nn < ci && kc < co) val = W[((size_t)kc * ci + nn) * taps + tap];
+            }
+        }
+        const float hi = __uint_as_float(__float_as_uint(val) & 0xFFFFE000u);
+        const float lo = val - hi;
+        float* base = out + blk * (size_t)(2 * bnt * 32);
+        const int pos = n * 32 + ((c ^ (n & 7)) << 2) + e;
+        base[pos] = hi;
+        base[bnt * 32 + pos] = lo;
+    }
+}
+
+void pick_tiles(int n_out, int* bnt, int* ntiles) {
+    int nt = (n_out + 255) / 256;
+    int per = (n_out + nt - 1) / nt;
+    per = (per + 15) & ~15;
+    *bnt = per;
+    *ntiles = nt;
+}
+
+}  // namespace
+
+extern "C" int selavi_conv_tiles(int n_out, int* bnt, int* ntiles) {
+    if (n_out <= 0 || !bnt || !ntiles) return selavi_fail(-1, "conv_tiles: bad arguments");
+    pick_tiles(n_out, bnt, ntiles);
+    return 0;
+}
+
+extern "C" size_t selavi_conv_wpack_bytes(int n_out, int k_total) {
+    int bnt, nt;
+    pick_tiles(n_out, &bnt, &nt);
+    const int kstages = (k_total + BK - 1) / BK;
+    return (size_t)nt * kstages * 2 * bnt * 128;
+}
+
+extern "C" int selavi_conv_pack_weights(const float* W, int mode, int co, int ci, int taps, int cs, void* wpack,
+                                        void* stream) {
+    if (!W || !wpack || co <= 0 || ci <= 0 || taps <= 0 || (cs & 3)) return selavi_fail(-1, "conv_pack_weights: bad arguments");
+    int bnt, nt;
+    pick_tiles(mode == 0 ? co : ci, &bnt, &nt);
+    const int kstages = (taps * cs + BK - 1) / BK;
+    const size_t total = (size_t)nt * kstages * bnt * 32;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    conv_pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, mode, co, ci, taps, cs, bnt, nt, kstages,
+                                                                       reinterpret_cast<float*>(wpack));
+    SV_CUDA_CHECK(cudaGetLastError(), "conv_pack_weights: launch");
+    return 0;
+}
+
+// geom: [mode, nb, ts, hs, ws, cs, td, hd, wd, cd, kt, kh, kw, st, sh, sw, pt, ph, pw, n_out]
+extern "C" int selavi_conv_gemm(const float* src, float* dst, const void* wpack, const int* geom, const float* pro_scale,
+                                const float* pro_shift, int pro_relu, float* stats_partial, int accumulate, int passes,
+                                void* stream) {
+    if (!src || !dst || !wpack || !geom) return selavi_fail(-1, "conv_gemm: null argument");
+    ConvParams p;
+    p.src = src;
+    p.dst = dst;
+    p.wpack = reinterpret_cast<const unsigned char*>(wpack);
+    p.pro_scale = pro_scale;
+    p.pro_shift = pro_shift;
+    p.stats = stats_partial;
+    p.mode = geom[0];
+    p.nb = geom[1]; p.ts = geom[2]; p.hs = geom[3]; p.ws = geom[4]; p.cs = geom[5];
+    p.td = geom[6]; p.hd = geom[7]; p.wd = geom[8]; p.cd = geom[9];
+    p.kt = geom[10]; p.kh = geom[11]; p.kw = geom[12];
+    p.st = geom[13]; p.sh = geom[14]; p.sw = geom[15];
+    p.pt = geom[16]; p.ph = geom[17]; p.pw = geom[18];
+    const int n_out = geom[19];
+    if ((p.cs & 3) || (p.cd & 3) || p.cs <= 0 || p.cd <= 0) return selavi_fail(-1, "conv_gemm: channel strides must be multiples of 4");
+    if (p.kt * p.kh * p.kw > MAX_TAPS) return selavi_fail(-1, "conv_gemm: too many taps");
+    if (p.td >= 1024 || p.hd >= 2048 || p.wd >= 1024) return selavi_fail(-1, "conv_gemm: spatial extent too large");
+    if ((p.st != 1 && p.st != 2) || (p.sh != 1 && p.sh != 2) || (p.sw != 1 && p.sw != 2)) return selavi_fail(-1, "conv_gemm: stride must be 1 or 2");
+    if (passes != 1 && passes != 3) return selavi_fail(-1, "conv_gemm: passes must be 1 or 3");
+    if ((pro_scale == nullptr) != (pro_shift == nullptr)) return selavi_fail(-1, "conv_gemm: prologue needs scale and shift");
+    const long long M = (long long)p.nb * p.td * p.hd * p.wd;
+    if (M <= 0 || M > 0x7fffffffLL || (long long)p.nb * p.ts * p.hs * p.ws > 0x7fffffffLL) return selavi_fail(-1, "conv_gemm: bad pixel count");
+    p.M = (int)M;
+    pick_tiles(n_out, &p.bnt, &p.ntiles);
+    // padded destination channels [n_out, cd) are written as exact zeros by the (zero) weight tile rows
+    if (p.ntiles * p.bnt < p.cd) return selavi_fail(-1, "conv_gemm: cd exceeds the tiled channel range");
+    p.kchunks = p.kt * p.kh * p.kw * (p.cs >> 2);
+    p.kstages = (p.kchunks + 7) / 8;
+    p.pro_relu = pro_relu;
+    p.accumulate = accumulate;
+    p.passes = passes;
+    uint32_t cols = 32;
+    while ((int)cols < p.bnt) cols <<= 1;
+    p.tmem_cols = cols;
+    const int stage_bytes = 2 * A_TILE_BYTES + 2 * p.bnt * 128;
+    const int tail_bytes = 8 * 8 * 2 + 8 + 8 + MAX_TAPS * 4 + LOADER_WARPS * 2 * 16 * 4 + 64;
+    int stages = (227 * 1024 - 1024 - tail_bytes) / stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages > p.kstages) stages = p.kstages < 1 ? 1 : p.kstages;
+    if (stages < 2 && p.kstages > 1) return selavi_fail(-1, "conv_gemm: tile does not fit shared memory");
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + tail_bytes + 1024;
+    SV_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                  "conv_gemm: cudaFuncSetAttribute");
+    dim3 grid((p.M + BM - 1) / BM, p.ntiles);
+    conv_igemm_kernel<<<grid, CONV_THREADS, smem, (cudaStream_t)stream>>>(p);
+    SV_CUDA_CHECK(cudaGetLastError(), "conv_gemm: launch");
+    return 0;
+}

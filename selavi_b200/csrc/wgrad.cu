@@ -1,0 +1,361 @@
+// Weight-gradient of the implicit-GEMM convolution on tcgen05 (the contraction runs over PIXELS).
+//
+//   dW[co, ci, tap] = sum_m  P(src)[pix(m, tap), ci] * dz[m, co]          (m = output pixel of the forward conv)
+//
+// Replaces cuDNN's wgrad behind every Conv3d/Conv2d of the reference model (model.py:93-121) in
+// loss.backward() (main.py:298).  GEMM view: rows = flattened (tap, ci) (128 per CTA), columns = co (BNt),
+// K = pixels.  Both operands are channels-last in HBM, i.e. MN-major for this GEMM: a pixel's 32 consecutive
+// channels are one 128-byte row of a SWIZZLE_128B MN-major atom (8 pixels deep = one tf32 MMA K step), so the
+// loaders store exactly what they load, no transpose.  The im2col gather, the fused BN+ReLU prologue of the
+// previous layer and the tf32 hi/lo split are done in registers like in conv.cu.  The pixel range is split
+// over CTAs (split-K); partial tiles go to a [slices][taps*cs][co] buffer that wgrad_reduce sums in a fixed
+// order and scatters into the torch weight layout (deterministic, no atomics).
+#include <stdint.h>
+
+#include "../../include/selavi_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int WG_LOADER_WARPS = 8;
+constexpr int WG_MMA_WARP = WG_LOADER_WARPS;
+constexpr int WG_THREADS = (WG_LOADER_WARPS + 1) * 32;
+constexpr int WG_PIX = 32;                     // pixels per stage (4 MMA K steps)
+constexpr int WG_A_BYTES = 4 * 4 * 1024;       // [4 k-groups][4 row chunks of 32] atoms of 1 KB
+
+struct WgradParams {
+    const float* src;   // forward input (raw), gathered
+    const float* dz;    // gradient wrt the conv output [M, cd]
+    float* partial;     // [slices][mtiles*128][ntiles*bnt]
+    const float* pro_scale;
+    const float* pro_shift;
+    int nb, ts, hs, ws, cs;
+    int td, hd, wd, cd;
+    int kt, kh, kw, st, sh, sw, pt, ph, pw;
+    int M;
+    int mtiles, bnt, ntiles, natom;   // natom = ceil(bnt/32)
+    int stages, total_kstages, kstages_per_slice;
+    int pro_relu, passes;
+    uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t wg_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+__device__ __forceinline__ void wg_st4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = 4 * p.natom * 1024;
+    const int stage_bytes = 2 * WG_A_BYTES + 2 * b_bytes;
+    unsigned char* tail = smem + (size_t)p.stages * stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* empty_bar = full_bar + 8;
+    uint64_t* accum_bar = empty_bar + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int mt = blockIdx.x % p.mtiles;
+    const int ntile = blockIdx.x / p.mtiles;
+    const int slice = blockIdx.y;
+    const int ks_begin = slice * p.kstages_per_slice;
+    int ks_end = ks_begin + p.kstages_per_slice;
+    if (ks_end > p.total_kstages) ks_end = p.total_kstages;
+    const int nks = ks_end - ks_begin;   // >= 1 by construction
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            sv::mbar_init(&full_bar[s], WG_LOADER_WARPS);
+            sv::mbar_init(&empty_bar[s], 1);
+        }
+        sv::mbar_init(accum_bar, 1);
+        sv::fence_barrier_init();
+    }
+    if (warp == WG_MMA_WARP) {
+        sv::tmem_alloc(tmem_slot, p.tmem_cols);
+        sv::tmem_relinquish();
+    }
+    sv::tc_fence_before();
+    __syncthreads();
+    sv::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < WG_LOADER_WARPS) {
+        // this thread's fixed GEMM-row chunk: flattened K chunk Q = mt*32 + lane -> (tap, c4)
+        const int C4 = p.cs >> 2;
+        const int taps = p.kt * p.kh * p.kw;
+        const int Q = mt * 32 + lane;
+        const int tap = Q / C4, c4 = Q % C4;
+        const bool qvalid = tap < taps;
+        const int kw_ = tap % p.kw, kh_ = (tap / p.kw) % p.kh, kt_ = tap / (p.kw * p.kh);
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sf = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool pro = p.pro_scale != nullptr;
+        if (pro && qvalid) {
+            sc = __ldg(reinterpret_cast<const float4*>(p.pro_scale + c4 * 4));
+            sf = __ldg(reinterpret_cast<const float4*>(p.pro_shift + c4 * 4));
+        }
+        const int prow = warp;  // pixel rows prow + 8*j within the stage; (p & 7) == warp
+        const int n_off = ntile * p.bnt;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int ks = ks_begin; ks < ks_end; ++ks) {
+            float4 xa[4];
+            bool oka[4];
+            float4 xb[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = ks * WG_PIX + prow + 8 * j;
+                xa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                xb[j][0] = xb[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                bool ok = false;
+                if (m < p.M) {
+                    const int w_ = m % p.wd;
+                    const int t1 = m / p.wd;
+                    const int h_ = t1 % p.hd;
+                    const int t2 = t1 / p.hd;
+                    const int t_ = t2 % p.td;
+                    const int n_ = t2 / p.td;
+                    const int a = t_ * p.st - p.pt + kt_;
+                    const int b = h_ * p.sh - p.ph + kh_;
+                    const int d = w_ * p.sw - p.pw + kw_;
+                    ok = qvalid & (a >= 0) & (a < p.ts) & (b >= 0) & (b < p.hs) & (d >= 0) & (d < p.ws);
+                    if (ok) {
+                        const size_t pix = (size_t)((n_ * p.ts + a) * p.hs + b) * p.ws + d;
+                        xa[j] = __ldg(reinterpret_cast<const float4*>(p.src + pix * p.cs + c4 * 4));
+                    }
+                    const float* zrow = p.dz + (size_t)m * p.cd + n_off;
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const int n4 = lane + 32 * jj;
+                        if (n4 * 4 < p.bnt && n_off + n4 * 4 < p.cd)
+                            xb[j][jj] = __ldg(reinterpret_cast<const float4*>(zrow + n4 * 4));
+                    }
+                }
+                oka[j] = ok;
+            }
+            sv::mbar_wait(&empty_bar[stage], phase ^ 1);
+            const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t a_lo = a_hi + WG_A_BYTES;
+            const uint32_t b_hi = a_lo + WG_A_BYTES;
+            const uint32_t b_lo = b_hi + b_bytes;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int pr = prow + 8 * j;     // pixel row in the stage, k-group = j, row in atom = prow
+                float4 x = xa[j];
+                if (pro && oka[j]) {
+                    x.x = fmaf(x.x, sc.x, sf.x);
+                    x.y = fmaf(x.y, sc.y, sf.y);
+                    x.z = fmaf(x.z, sc.z, sf.z);
+                    x.w = fmaf(x.w, sc.w, sf.w);
+                    if (p.pro_relu) {
+                        x.x = fmaxf(x.x, 0.f);
+                        x.y = fmaxf(x.y, 0.f);
+                        x.z = fmaxf(x.z, 0.f);
+                        x.w = fmaxf(x.w, 0.f);
+                    }
+                }
+                {
+                    const uint32_t off = (uint32_t)(((pr >> 3) * 4 + (lane >> 3)) * 1024 + (pr & 7) * 128 +
+                                                    (((lane & 7) ^ (pr & 7)) << 4));
+                    const uint32_t h0 = wg_hi(x.x), h1 = wg_hi(x.y), h2 = wg_hi(x.z), h3 = wg_hi(x.w);
+                    wg_st4(a_hi + off, h0, h1, h2, h3);
+                    if (p.passes == 3)
+                        wg_st4(a_lo + off, __float_as_uint(x.x - __uint_as_float(h0)), __float_as_uint(x.y - __uint_as_float(h1)),
+                               __float_as_uint(x.z - __uint_as_float(h2)), __float_as_uint(x.w - __uint_as_float(h3)));
+                }
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int n4 = lane + 32 * jj;
+                    if (n4 < p.natom * 8) {
+                        const float4 z = xb[j][jj];
+                        const uint32_t off = (uint32_t)(((pr >> 3) * p.natom + (n4 >> 3)) * 1024 + (pr & 7) * 128 +
+                                                        (((n4 & 7) ^ (pr & 7)) << 4));
+                        const uint32_t h0 = wg_hi(z.x), h1 = wg_hi(z.y), h2 = wg_hi(z.z), h3 = wg_hi(z.w);
+                        wg_st4(b_hi + off, h0, h1, h2, h3);
+                        if (p.passes == 3)
+                            wg_st4(b_lo + off, __float_as_uint(z.x - __uint_as_float(h0)), __float_as_uint(z.y - __uint_as_float(h1)),
+                                   __float_as_uint(z.z - __uint_as_float(h2)), __float_as_uint(z.w - __uint_as_float(h3)));
+                    }
+                }
+            }
+            sv::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) sv::mbar_arrive(&full_bar[stage]);
+            if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+
+        // ---- epilogue: TMEM -> partial[slice][mt*128 + row][ntile*bnt + col]
+        sv::mbar_wait(accum_bar, 0);
+        sv::tc_fence_after();
+        const int quad = warp & 3, half = warp >> 2;
+        const int units = p.bnt >> 4;
+        const int u_begin = half == 0 ? 0 : (units + 1) / 2;
+        const int u_end = half == 0 ? (units + 1) / 2 : units;
+        const int row = quad * 32 + lane;
+        const int ntot = p.ntiles * p.bnt;
+        float* out_row = p.partial + ((size_t)slice * (p.mtiles * 128) + mt * 128 + row) * ntot + n_off;
+        for (int u = u_begin; u < u_end; ++u) {
+            uint32_t acc[16];
+            sv::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(u * 16), acc);
+            sv::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                *reinterpret_cast<float4*>(out_row + u * 16 + i) =
+                    make_float4(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]),
+                                __uint_as_float(acc[i + 3]));
+            }
+        }
+        sv::tc_fence_before();
+    } else {
+        if (lane == 0) {
+            const uint32_t idesc = sv::make_idesc_tf32(128, p.bnt, 1, 1);  // both operands MN-major
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t b_sbo = (uint32_t)(p.natom * 1024);
+            for (int i = 0; i < nks; ++i) {
+                sv::mbar_wait(&full_bar[stage], phase);
+                sv::tc_fence_after();
+                const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t a_lo = a_hi + WG_A_BYTES;
+                const uint32_t b_hi = a_lo + WG_A_BYTES;
+                const uint32_t b_lo = b_hi + b_bytes;
+#pragma unroll
+                for (int kg = 0; kg < 4; ++kg) {
+                    const uint64_t da_hi = sv::make_smem_desc(a_hi + kg * 4096, 1024, 4096, 2);
+                    const uint64_t db_hi = sv::make_smem_desc(b_hi + kg * b_sbo, 1024, b_sbo, 2);
+                    if (p.passes == 3) {
+                        const uint64_t da_lo = sv::make_smem_desc(a_lo + kg * 4096, 1024, 4096, 2);
+                        const uint64_t db_lo = sv::make_smem_desc(b_lo + kg * b_sbo, 1024, b_sbo, 2);
+                        sv::umma_tf32(tmem_base, da_lo, db_hi, idesc, (i | kg) ? 1u : 0u);
+                        sv::umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
+                        sv::umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
+                    } else {
+                        sv::umma_tf32(tmem_base, da_hi, db_hi, idesc, (i | kg) ? 1u : 0u);
+                    }
+                }
+                sv::umma_commit(&empty_bar[stage]);
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            sv::umma_commit(accum_bar);
+        }
+    }
+    __syncthreads();
+    if (warp == WG_MMA_WARP) {
+        sv::tc_fence_after();
+        sv::tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// dW[co][ci][tap] (+)= sum_s partial[s][tap*cs + ci][co]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int slices, int mg_pad, int ntot, int co, int ci,
+                                    int taps, int cs, float* __restrict__ dW, int accumulate) {
+    const size_t total = (size_t)co * ci * taps;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        // co fastest for coalesced reads of the partial tiles
+        const int o = (int)(idx % co);
+        const size_t r = idx / co;
+        const int c = (int)(r % ci);
+        const int tap = (int)(r / ci);
+        const size_t row = (size_t)tap * cs + c;
+        float s = 0.f;
+        for (int k = 0; k < slices; ++k) s += partial[((size_t)k * mg_pad + row) * ntot + o];
+        float* dst = dW + ((size_t)o * ci + c) * taps + tap;
+        *dst = accumulate ? (*dst + s) : s;
+    }
+}
+
+void wg_tiles(int n_out, int* bnt, int* ntiles) {
+    int nt = (n_out + 255) / 256;
+    int per = (n_out + nt - 1) / nt;
+    per = (per + 15) & ~15;
+    *bnt = per;
+    *ntiles = nt;
+}
+
+struct WgPlan {
+    int mtiles, bnt, ntiles, natom, total_kstages, slices, kstages_per_slice;
+};
+
+WgPlan wg_plan(int co, int taps, int cs, long long M) {
+    WgPlan pl;
+    wg_tiles(co, &pl.bnt, &pl.ntiles);
+    pl.natom = (pl.bnt + 31) / 32;
+    pl.mtiles = (taps * cs + 127) / 128;
+    pl.total_kstages = (int)((M + WG_PIX - 1) / WG_PIX);
+    const int tiles = pl.mtiles * pl.ntiles;
+    int slices = (148 * 3 + tiles - 1) / tiles;  // about 3 waves of CTAs
+    if (slices > pl.total_kstages) slices = pl.total_kstages;
+    if (slices > 256) slices = 256;
+    if (slices < 1) slices = 1;
+    pl.kstages_per_slice = (pl.total_kstages + slices - 1) / slices;
+    pl.slices = (pl.total_kstages + pl.kstages_per_slice - 1) / pl.kstages_per_slice;
+    return pl;
+}
+
+}  // namespace
+
+extern "C" size_t selavi_wgrad_workspace_bytes(int co, int taps, int cs, long long M) {
+    const WgPlan pl = wg_plan(co, taps, cs, M);
+    return (size_t)pl.slices * pl.mtiles * 128 * pl.ntiles * pl.bnt * sizeof(float);
+}
+
+// geom: same 20 ints as selavi_conv_gemm with mode 0 (the FORWARD geometry of the convolution); dz is [M, cd].
+extern "C" int selavi_conv_wgrad(const float* src, const float* dz, float* dW, const int* geom, int ci_real,
+                                 const float* pro_scale, const float* pro_shift, int pro_relu, void* workspace,
+                                 int accumulate, int passes, void* stream) {
+    if (!src || !dz || !dW || !geom || !workspace) return selavi_fail(-1, "conv_wgrad: null argument");
+    WgradParams p;
+    p.src = src;
+    p.dz = dz;
+    p.partial = reinterpret_cast<float*>(workspace);
+    p.pro_scale = pro_scale;
+    p.pro_shift = pro_shift;
+    p.nb = geom[1]; p.ts = geom[2]; p.hs = geom[3]; p.ws = geom[4]; p.cs = geom[5];
+    p.td = geom[6]; p.hd = geom[7]; p.wd = geom[8]; p.cd = geom[9];
+    p.kt = geom[10]; p.kh = geom[11]; p.kw = geom[12];
+    p.st = geom[13]; p.sh = geom[14]; p.sw = geom[15];
+    p.pt = geom[16]; p.ph = geom[17]; p.pw = geom[18];
+    const int co = geom[19];
+    if ((p.cs & 3) || (p.cd & 3)) return selavi_fail(-1, "conv_wgrad: channel strides must be multiples of 4");
+    if (passes != 1 && passes != 3) return selavi_fail(-1, "conv_wgrad: passes must be 1 or 3");
+    if ((pro_scale == nullptr) != (pro_shift == nullptr)) return selavi_fail(-1, "conv_wgrad: prologue needs scale and shift");
+    const long long M = (long long)p.nb * p.td * p.hd * p.wd;
+    if (M <= 0 || M > 0x7fffffffLL) return selavi_fail(-1, "conv_wgrad: bad pixel count");
+    p.M = (int)M;
+    const int taps = p.kt * p.kh * p.kw;
+    const WgPlan pl = wg_plan(co, taps, p.cs, M);
+    p.mtiles = pl.mtiles; p.bnt = pl.bnt; p.ntiles = pl.ntiles; p.natom = pl.natom;
+    p.total_kstages = pl.total_kstages; p.kstages_per_slice = pl.kstages_per_slice;
+    p.pro_relu = pro_relu;
+    p.passes = passes;
+    uint32_t cols = 32;
+    while ((int)cols < p.bnt) cols <<= 1;
+    p.tmem_cols = cols;
+    const int stage_bytes = 2 * WG_A_BYTES + 2 * 4 * p.natom * 1024;
+    const int tail_bytes = 8 * 8 * 2 + 8 + 8 + 64;
+    int stages = (227 * 1024 - 1024 - tail_bytes) / stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages < 2) return selavi_fail(-1, "conv_wgrad: tile does not fit shared memory");
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + tail_bytes + 1024;
+    SV_CUDA_CHECK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                  "conv_wgrad: cudaFuncSetAttribute");
+    dim3 grid(pl.mtiles * pl.ntiles, pl.slices);
+    wgrad_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(p);
+    SV_CUDA_CHECK(cudaGetLastError(), "conv_wgrad: launch");
+    const size_t total = (size_t)co * ci_real * taps;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wgrad_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p.partial, pl.slices, pl.mtiles * 128, pl.ntiles * pl.bnt,
+                                                                  co, ci_real, taps, p.cs, dW, accumulate);
+    SV_CUDA_CHECK(cudaGetLastError(), "conv_wgrad: reduce launch");
+    return 0;
+}

@@ -1,0 +1,146 @@
+"""Thin checked Python wrappers over the C-ABI kernels (one function per entry point of include/selavi_b200.h).
+
+Tensors are torch CUDA tensors used purely as device memory; every function launches on the current stream
+and returns without synchronising.  Activations are channels-last fp32 `[N, T, H, W, Cs]` with `Cs` = channel
+count padded to a multiple of 4 (pad channels are zero).  No CPU fallback: a missing library raises.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def pad4(c):
+    return (c + 3) & ~3
+
+
+def to_channels_last(x):
+    """[N,C,T,H,W] or [N,C,H,W] (any float dtype) -> contiguous fp32 [N,T,H,W,pad4(C)]."""
+    if x.dim() == 4:
+        x = x.unsqueeze(2)
+    n, c, t, h, w = x.shape
+    out = torch.zeros((n, t, h, w, pad4(c)), dtype=torch.float32, device=x.device)
+    out[..., :c] = x.permute(0, 2, 3, 4, 1)
+    return out
+
+
+def from_channels_last(x_cl, c):
+    """[N,T,H,W,Cs] -> [N,C,T,H,W]."""
+    return x_cl[..., :c].permute(0, 4, 1, 2, 3).contiguous()
+
+
+class ConvGeom:
+    """Forward geometry of one convolution (3-D; 2-D convs use T=1, kt=1)."""
+
+    def __init__(self, nb, ci, co, in_thw, kernel, stride, padding):
+        self.nb, self.ci, self.co = nb, ci, co
+        self.ti, self.hi, self.wi = in_thw
+        self.kt, self.kh, self.kw = kernel
+        self.st, self.sh, self.sw = stride
+        self.pt, self.ph, self.pw = padding
+        self.to = (self.ti + 2 * self.pt - self.kt) // self.st + 1
+        self.ho = (self.hi + 2 * self.ph - self.kh) // self.sh + 1
+        self.wo = (self.wi + 2 * self.pw - self.kw) // self.sw + 1
+        self.cis, self.cos = pad4(ci), pad4(co)
+        self.taps = self.kt * self.kh * self.kw
+        self.m_out = nb * self.to * self.ho * self.wo
+        self.m_in = nb * self.ti * self.hi * self.wi
+
+    def arr(self, mode):
+        if mode == 0:
+            g = [0, self.nb, self.ti, self.hi, self.wi, self.cis, self.to, self.ho, self.wo, self.cos,
+                 self.kt, self.kh, self.kw, self.st, self.sh, self.sw, self.pt, self.ph, self.pw, self.co]
+        else:
+            g = [1, self.nb, self.to, self.ho, self.wo, self.cos, self.ti, self.hi, self.wi, self.cis,
+                 self.kt, self.kh, self.kw, self.st, self.sh, self.sw, self.pt, self.ph, self.pw, self.ci]
+        return (ctypes.c_int * 20)(*g)
+
+    def out_shape(self):
+        return (self.nb, self.to, self.ho, self.wo, self.cos)
+
+    def in_shape(self):
+        return (self.nb, self.ti, self.hi, self.wi, self.cis)
+
+
+def conv_tiles(n_out):
+    bnt, nt = ctypes.c_int(), ctypes.c_int()
+    _lib.check(_lib.lib().selavi_conv_tiles(n_out, ctypes.byref(bnt), ctypes.byref(nt)), "selavi_conv_tiles")
+    return bnt.value, nt.value
+
+
+def pack_weights(w, geom, mode, out=None):
+    """w: torch weight [co, ci, kt, kh, kw] (or [co, ci, kh, kw]) fp32 CUDA -> packed B operand (uint8 buffer)."""
+    w = w.detach()
+    if not (w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()):
+        raise ValueError("weight must be a contiguous fp32 CUDA tensor")
+    lib = _lib.lib()
+    n_out, cs = (geom.co, geom.cis) if mode == 0 else (geom.ci, geom.cos)
+    nbytes = lib.selavi_conv_wpack_bytes(n_out, geom.taps * cs)
+    if out is None:
+        out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    elif out.numel() != nbytes:
+        raise ValueError("packed weight buffer has the wrong size")
+    with torch.cuda.device(w.device):
+        _lib.check(lib.selavi_conv_pack_weights(_lib.ptr(w), mode, geom.co, geom.ci, geom.taps, cs, _lib.ptr(out),
+                                                _lib.stream_ptr()), "selavi_conv_pack_weights")
+    return out
+
+
+def stats_buffer(geom, device):
+    bnt, nt = conv_tiles(geom.co)
+    return torch.empty(((geom.m_out + 127) // 128, 2, bnt * nt), dtype=torch.float32, device=device)
+
+
+def _chk(t, shape, name):
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == tuple(shape)):
+        raise ValueError(f"{name}: expected contiguous fp32 CUDA tensor of shape {tuple(shape)}, got {tuple(t.shape)} {t.dtype}")
+
+
+def conv_forward(x, wpack, geom, out=None, scale=None, shift=None, relu=False, stats=None, passes=3):
+    _chk(x, geom.in_shape(), "x")
+    if out is None:
+        out = torch.empty(geom.out_shape(), dtype=torch.float32, device=x.device)
+    _chk(out, geom.out_shape(), "out")
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().selavi_conv_gemm(_lib.ptr(x), _lib.ptr(out), _lib.ptr(wpack), geom.arr(0), _lib.ptr(scale),
+                                               _lib.ptr(shift), 1 if relu else 0, _lib.ptr(stats), 0, passes,
+                                               _lib.stream_ptr()), "selavi_conv_gemm(fwd)")
+    return out
+
+
+def conv_dgrad(dz, wpack_t, geom, out=None, accumulate=False, passes=3):
+    _chk(dz, geom.out_shape(), "dz")
+    if out is None:
+        out = torch.empty(geom.in_shape(), dtype=torch.float32, device=dz.device)
+        accumulate = False
+    _chk(out, geom.in_shape(), "dx")
+    with torch.cuda.device(dz.device):
+        _lib.check(_lib.lib().selavi_conv_gemm(_lib.ptr(dz), _lib.ptr(out), _lib.ptr(wpack_t), geom.arr(1), None, None, 0,
+                                               None, 1 if accumulate else 0, passes, _lib.stream_ptr()),
+                   "selavi_conv_gemm(dgrad)")
+    return out
+
+
+_wgrad_ws = {}
+
+
+def conv_wgrad(x, dz, geom, dw, scale=None, shift=None, relu=False, accumulate=False, passes=3):
+    """dw: torch-layout gradient buffer [co, ci, kt, kh, kw] fp32, written (or accumulated into)."""
+    _chk(x, geom.in_shape(), "x")
+    _chk(dz, geom.out_shape(), "dz")
+    if not (dw.is_cuda and dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == geom.co * geom.ci * geom.taps):
+        raise ValueError("dw must be a contiguous fp32 CUDA tensor in the torch weight layout")
+    lib = _lib.lib()
+    nbytes = lib.selavi_wgrad_workspace_bytes(geom.co, geom.taps, geom.cis, geom.m_out)
+    key = (x.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _wgrad_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _wgrad_ws[key] = ws
+    with torch.cuda.device(x.device):
+        _lib.check(lib.selavi_conv_wgrad(_lib.ptr(x), _lib.ptr(dz), _lib.ptr(dw), geom.arr(0), geom.ci, _lib.ptr(scale),
+                                         _lib.ptr(shift), 1 if relu else 0, _lib.ptr(ws), 1 if accumulate else 0, passes,
+                                         _lib.stream_ptr()), "selavi_conv_wgrad")
+    return dw
