@@ -80,6 +80,80 @@ int selavi_conv_wgrad(const float* src, const float* dz, float* dW, const int* g
                       int passes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * BatchNorm (train mode, nn.BatchNorm{1,2,3}d / SyncBatchNorm semantics), residual add, ReLU, pooling, layout,
+ * SGD.  Activations channels-last fp32 [M, cs]; per-channel vectors have cs (padded) entries.
+ *   reduce_partials: conv-epilogue tile partials [tiles][2][ctot] -> fp64 sums [2][cs] (sum, sum of squares)
+ *   finalize:        sums over `count` elements (all ranks) -> scale = gamma*invstd, shift = beta - mean*scale,
+ *                    saved mean / invstd, running-stat update (momentum, unbiased variance)
+ *   apply:           out = act(z*scale+shift [+ res | + res*rscale+rshift])  (tv:video/resnet.py:107-119)
+ *   bwd_reduce:      sums [2][cs] = (sum g, sum g*zhat), g masked by the following ReLU:
+ *                    mask_mode 0 none, 1 act>0 (materialised block output), 2 z*scale+shift>0
+ *   bwd_apply:       dz = scale*(g - sum_g/count - zhat*sum_gz/count); optional gres (+)= masked g
+ */
+int selavi_bn_reduce_partials(const float* partial, int tiles, int ctot, int cs, double* sums, void* stream);
+int selavi_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, float momentum, float eps, int c_real, int cs, float* scale, float* shift,
+                       float* mean, float* invstd, int update_running, void* stream);
+int selavi_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                          float eps, int c_real, int cs, float* scale, float* shift, void* stream);
+int selavi_bn_apply(const float* z, const float* scale, const float* shift, const float* res, const float* rscale,
+                    const float* rshift, int relu, float* out, long long M, int cs, void* stream);
+int selavi_bn_bwd_blocks(long long M);
+int selavi_bn_bwd_reduce(const float* g, const float* z, const float* act, int mask_mode, const float* scale,
+                         const float* shift, const float* mean, const float* invstd, long long M, int cs, float* partial,
+                         double* sums, void* stream);
+int selavi_bn_bwd_apply(const float* g, const float* z, const float* act, int mask_mode, const float* scale,
+                        const float* shift, const float* mean, const float* invstd, const double* sums, double count,
+                        long long M, int cs, float* dz, float* gres, int gres_accumulate, void* stream);
+int selavi_relu_bwd(const float* g, const float* act, float* out, long long n, int accumulate, void* stream);
+/* MaxPool2d(3,2,1) over relu(z*scale+shift) (tv:resnet.py:268-271) and its gradient wrt that activation */
+int selavi_maxpool3x3s2_fwd(const float* z, const float* scale, const float* shift, float* out, int nb, int h, int w,
+                            int cs, void* stream);
+int selavi_maxpool3x3s2_bwd(const float* dout, const float* z, const float* scale, const float* shift, float* da, int nb,
+                            int h, int w, int cs, void* stream);
+/* AdaptiveAvgPool(1): y [nb, P, cs] -> feat [nb, c_real] and back */
+int selavi_avgpool_fwd(const float* y, float* feat, int nb, int P, int cs, int c_real, void* stream);
+int selavi_avgpool_bwd(const float* dfeat, float* dy, int nb, int P, int cs, int c_real, void* stream);
+/* [nb, C, P] (NCDHW) -> channels-last [nb, P, cs] with zero pad channels */
+int selavi_nchw_to_cl(const float* x, float* out, int nb, int C, long long P, int cs, void* stream);
+/* fused multi-tensor torch.optim.SGD step (main.py:132-137,302); table = device array of {p, g, buf, n} */
+int selavi_sgd_step(const void* table, int n_tensors, float lr, float momentum, float weight_decay, int first_step,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Projection heads (model.py:62-90 MLPv2 / nn.Linear heads, model.py:201-252) and cross-entropy
+ * (utils.py:377-387), batched over the H heads of a modality.  *_tbl = device arrays of H pointers to the
+ * per-head nn.Parameter storage (parameters stay ordinary tensors).
+ *   bgemm: C[h](m,n) (+)= sum_k A[h](m,k)*Amask[h](m,k)*B[h](k,n) + bias[h](n), arbitrary element strides.
+ *   heads_bn_*: BatchNorm1d over the batch rows of z [H,B,F] (train: batch stats / eval: running stats),
+ *               heads_act: a = relu(z*scale+shift)*mask (mask = dropout mask/(1-p) or NULL).
+ *   ce_loss: loss_rows[h,b] = logsumexp(x) - x[label[b,h]], loss_mean = mean over (h,b) = get_loss();
+ *            dlogits [H,B,K] = (softmax - onehot) * grad_scale (nullable).
+ */
+int selavi_bgemm(int H, int M, int N, int K, const float* A, const void* const* A_tbl, long long a_bs, long long a_sm,
+                 long long a_sk, const float* Amask, long long am_bs, const float* B, const void* const* B_tbl,
+                 long long b_bs, long long b_sk, long long b_sn, const float* bias, const void* const* bias_tbl,
+                 long long bias_bs, float* C, long long c_bs, long long c_sm, long long c_sn, int accumulate, void* stream);
+int selavi_heads_bn_stats(const float* z, int H, int B, int F, double* sums, void* stream);
+int selavi_heads_bn_finalize(const double* sums, double count, const void* const* gamma_tbl, const void* const* beta_tbl,
+                             const void* const* rmean_tbl, const void* const* rvar_tbl, float momentum, float eps, int H,
+                             int F, float* scale, float* shift, float* mean, float* invstd, int update_running, void* stream);
+int selavi_heads_bn_eval_affine(const void* const* gamma_tbl, const void* const* beta_tbl, const void* const* rmean_tbl,
+                                const void* const* rvar_tbl, float eps, int H, int F, float* scale, float* shift,
+                                void* stream);
+int selavi_heads_act(const float* z, const float* scale, const float* shift, const float* mask, float* a, int H, int B,
+                     int F, void* stream);
+int selavi_heads_bn_bwd_reduce(const float* da, const float* mask, const float* z, const float* scale, const float* shift,
+                               const float* mean, const float* invstd, int H, int B, int F, double* sums, void* stream);
+int selavi_heads_bn_bwd_apply(const float* da, const float* mask, const float* z, const float* scale, const float* shift,
+                              const float* mean, const float* invstd, const double* sums, double count, int H, int B, int F,
+                              float* dz, void* stream);
+int selavi_heads_sum_masked(const float* x, const float* mask, float* out, int H, long long BF, int accumulate, void* stream);
+int selavi_heads_colsum(const float* x, float* out, int H, int M, int N, void* stream);
+int selavi_ce_loss(const void* const* logit_tbl, const long long* labels, long long lab_stride_b, long long lab_stride_h,
+                   int H, int B, int K, float grad_scale, float* loss_rows, float* loss_mean, float* dlogits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Symmetric peer-mapped buffers (CUDA IPC), the transport of the in-kernel NVSwitch exchange.
  * alloc: cudaMalloc + zero + export a 64-byte handle; open/close: map / unmap a peer's handle.
  */
@@ -88,6 +162,14 @@ int selavi_symm_open(const unsigned char* handle64, void** ptr_out);
 int selavi_symm_close(void* ptr);
 int selavi_symm_free(void* ptr);
 int selavi_symm_memset(void* ptr, int value, size_t bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Diagnostics: issue n_mma tcgen05.mma.kind::tf32 instructions on host-provided raw shared-memory operand
+ * images / descriptor bits and dump the 128 x N fp32 accumulator (tools/umma_probe.py).
+ */
+int selavi_debug_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
+                            unsigned long long adesc_base, unsigned long long bdesc_base, unsigned idesc, int n_mma,
+                            const unsigned* a_offs, const unsigned* b_offs, int N, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,45 @@ SIGNATURES = {
     "selavi_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_ll]),
     "selavi_conv_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                   c_int, c_int, c_void_p]),
+    "selavi_bn_reduce_partials": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "selavi_bn_finalize": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int,
+                                   c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "selavi_bn_eval_affine": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p,
+                                      c_void_p]),
+    "selavi_bn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_int,
+                                c_void_p]),
+    "selavi_bn_bwd_blocks": (c_int, [c_ll]),
+    "selavi_bn_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_ll,
+                                     c_int, c_void_p, c_void_p, c_void_p]),
+    "selavi_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_double, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "selavi_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "selavi_maxpool3x3s2_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "selavi_maxpool3x3s2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                        c_void_p]),
+    "selavi_avgpool_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "selavi_avgpool_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "selavi_nchw_to_cl": (c_int, [c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p]),
+    "selavi_sgd_step": (c_int, [c_void_p, c_int, c_float, c_float, c_float, c_int, c_void_p]),
+    "selavi_bgemm": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_ll, c_ll, c_ll, c_void_p, c_ll, c_void_p,
+                             c_void_p, c_ll, c_ll, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_ll, c_int,
+                             c_void_p]),
+    "selavi_heads_bn_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "selavi_heads_bn_finalize": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float,
+                                         c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "selavi_heads_bn_eval_affine": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p,
+                                            c_void_p, c_void_p]),
+    "selavi_heads_act": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "selavi_heads_bn_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                           c_int, c_int, c_void_p, c_void_p]),
+    "selavi_heads_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_double, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "selavi_heads_sum_masked": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p]),
+    "selavi_heads_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "selavi_ce_loss": (c_int, [c_void_p, c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                               c_void_p]),
+    "selavi_debug_umma_probe": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.c_ulonglong, ctypes.c_ulonglong,
+                                        ctypes.c_uint, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "selavi_symm_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
     "selavi_symm_open": (c_int, [c_void_p, c_void_p]),
     "selavi_symm_close": (c_int, [c_void_p]),

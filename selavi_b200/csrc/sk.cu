@@ -340,7 +340,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sk_kernel(const SkArgs a) {
         if (!is_producer) {
 #pragma unroll
             for (int i = 0; i < KPL; ++i) s_red[warp * Ks + lane + 32 * i] = acc[i];
-            s_red[warp * Ks + Kp + lane] = (lane == 0) ? err_acc : (lane == 1 ? cost_acc : 0.0);
+            const double cost0 = __shfl_sync(0xffffffffu, cost_acc, 0);  // err/cost are accumulated by lane 0
+            s_red[warp * Ks + Kp + lane] = (lane == 0) ? err_acc : (lane == 1 ? cost0 : 0.0);
         }
         __syncthreads();
         for (int k = tid; k < Ks; k += SK_THREADS) {

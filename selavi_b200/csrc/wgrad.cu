@@ -4,10 +4,11 @@
 //
 // Replaces cuDNN's wgrad behind every Conv3d/Conv2d of the reference model (model.py:93-121) in
 // loss.backward() (main.py:298).  GEMM view: rows = flattened (tap, ci) (128 per CTA), columns = co (BNt),
-// K = pixels.  Both operands are channels-last in HBM, i.e. MN-major for this GEMM: a pixel's 32 consecutive
-// channels are one 128-byte row of a SWIZZLE_128B MN-major atom (8 pixels deep = one tf32 MMA K step), so the
-// loaders store exactly what they load, no transpose.  The im2col gather, the fused BN+ReLU prologue of the
-// previous layer and the tf32 hi/lo split are done in registers like in conv.cu.  The pixel range is split
+// K = pixels.  Both operands are channels-last in HBM, i.e. MN-major for this GEMM.  tcgen05.mma.kind::tf32
+// returned all-zero accumulators for every MN-major descriptor variant probed on B200 (tools/umma_probe.py,
+// profiles/r01_umma_probe.txt), so the loaders transpose 4 pixels x 4 channels in registers and store K-major
+// SWIZZLE_128B tiles (a 128-byte row = 32 consecutive pixels of one channel).  The im2col gather, the fused
+// BN+ReLU prologue of the previous layer and the tf32 hi/lo split are done in registers like in conv.cu.  The pixel range is split
 // over CTAs (split-K); partial tiles go to a [slices][taps*cs][co] buffer that wgrad_reduce sums in a fixed
 // order and scatters into the torch weight layout (deterministic, no atomics).
 #include <stdint.h>
@@ -22,7 +23,7 @@ constexpr int WG_LOADER_WARPS = 8;
 constexpr int WG_MMA_WARP = WG_LOADER_WARPS;
 constexpr int WG_THREADS = (WG_LOADER_WARPS + 1) * 32;
 constexpr int WG_PIX = 32;                     // pixels per stage (4 MMA K steps)
-constexpr int WG_A_BYTES = 4 * 4 * 1024;       // [4 k-groups][4 row chunks of 32] atoms of 1 KB
+constexpr int WG_A_BYTES = 128 * 128;          // 128 GEMM rows x 128 B (32 pixels), K-major SWIZZLE_128B
 
 struct WgradParams {
     const float* src;   // forward input (raw), gathered
@@ -45,10 +46,35 @@ __device__ __forceinline__ void wg_st4(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// 4x4 register transpose: in r[i] = (channel c+0..3) of pixel i  ->  out r[i] = (pixel 0..3) of channel c+i
+__device__ __forceinline__ void transpose4(float4 (&r)[4]) {
+    const float4 a = r[0], b = r[1], c = r[2], d = r[3];
+    r[0] = make_float4(a.x, b.x, c.x, d.x);
+    r[1] = make_float4(a.y, b.y, c.y, d.y);
+    r[2] = make_float4(a.z, b.z, c.z, d.z);
+    r[3] = make_float4(a.w, b.w, c.w, d.w);
+}
+
+// store 4 GEMM rows (row0..row0+3), 16-byte chunk `pg` (4 consecutive pixels) of a K-major SW128 tile, hi (+lo)
+__device__ __forceinline__ void store_rows4(uint32_t hi_base, uint32_t lo_base, int row0, int pg, const float4 (&r)[4],
+                                            bool with_lo) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = row0 + i;
+        const uint32_t off = (uint32_t)(row * 128 + ((pg ^ (row & 7)) << 4));
+        const uint32_t h0 = wg_hi(r[i].x), h1 = wg_hi(r[i].y), h2 = wg_hi(r[i].z), h3 = wg_hi(r[i].w);
+        wg_st4(hi_base + off, h0, h1, h2, h3);
+        if (with_lo)
+            wg_st4(lo_base + off, __float_as_uint(r[i].x - __uint_as_float(h0)), __float_as_uint(r[i].y - __uint_as_float(h1)),
+                   __float_as_uint(r[i].z - __uint_as_float(h2)), __float_as_uint(r[i].w - __uint_as_float(h3)));
+    }
+}
+
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int b_bytes = 4 * p.natom * 1024;
+    // stage: A_hi [128 rows x 128B] | A_lo | B_hi [bnt rows x 128B] | B_lo ; a 128B row = 32 pixels (K-major)
+    const int b_bytes = p.bnt * 128;
     const int stage_bytes = 2 * WG_A_BYTES + 2 * b_bytes;
     unsigned char* tail = smem + (size_t)p.stages * stage_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
@@ -81,12 +107,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams 
     __syncthreads();
     sv::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int n_off = ntile * p.bnt;
 
     if (warp < WG_LOADER_WARPS) {
-        // this thread's fixed GEMM-row chunk: flattened K chunk Q = mt*32 + lane -> (tap, c4)
+        // thread -> (pixel group pg: 4 consecutive pixels, channel group cg: 4 consecutive GEMM rows)
+        const int pg = tid & 7;
+        const int cg = tid >> 3;  // 0..31 : A rows 4cg..4cg+3 ; B rows 4cg.. and 4(cg+32)..
         const int C4 = p.cs >> 2;
         const int taps = p.kt * p.kh * p.kw;
-        const int Q = mt * 32 + lane;
+        const int Q = mt * 32 + cg;          // flattened K chunk (tap, c4) of this thread's A rows
         const int tap = Q / C4, c4 = Q % C4;
         const bool qvalid = tap < taps;
         const int kw_ = tap % p.kw, kh_ = (tap / p.kw) % p.kh, kt_ = tap / (p.kw * p.kh);
@@ -96,90 +125,77 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams 
             sc = __ldg(reinterpret_cast<const float4*>(p.pro_scale + c4 * 4));
             sf = __ldg(reinterpret_cast<const float4*>(p.pro_shift + c4 * 4));
         }
-        const int prow = warp;  // pixel rows prow + 8*j within the stage; (p & 7) == warp
-        const int n_off = ntile * p.bnt;
+        const int nb_blocks = (p.bnt >> 2);   // B channel groups
         int stage = 0;
         uint32_t phase = 0;
         for (int ks = ks_begin; ks < ks_end; ++ks) {
-            float4 xa[4];
-            bool oka[4];
-            float4 xb[4][2];
+            float4 xa[4], xb0[4], xb1[4];
+            const int mbase = ks * WG_PIX + pg * 4;
+            int w_ = 0, h_ = 0, t_ = 0, n_ = 0;
+            if (mbase < p.M) {
+                w_ = mbase % p.wd;
+                const int t1 = mbase / p.wd;
+                h_ = t1 % p.hd;
+                const int t2 = t1 / p.hd;
+                t_ = t2 % p.td;
+                n_ = t2 / p.td;
+            }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int m = ks * WG_PIX + prow + 8 * j;
-                xa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                xb[j][0] = xb[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                bool ok = false;
+            for (int i = 0; i < 4; ++i) {
+                const int m = mbase + i;
+                xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                xb0[i] = xb1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (m < p.M) {
-                    const int w_ = m % p.wd;
-                    const int t1 = m / p.wd;
-                    const int h_ = t1 % p.hd;
-                    const int t2 = t1 / p.hd;
-                    const int t_ = t2 % p.td;
-                    const int n_ = t2 / p.td;
                     const int a = t_ * p.st - p.pt + kt_;
                     const int b = h_ * p.sh - p.ph + kh_;
                     const int d = w_ * p.sw - p.pw + kw_;
-                    ok = qvalid & (a >= 0) & (a < p.ts) & (b >= 0) & (b < p.hs) & (d >= 0) & (d < p.ws);
+                    const bool ok = qvalid & (a >= 0) & (a < p.ts) & (b >= 0) & (b < p.hs) & (d >= 0) & (d < p.ws);
                     if (ok) {
                         const size_t pix = (size_t)((n_ * p.ts + a) * p.hs + b) * p.ws + d;
-                        xa[j] = __ldg(reinterpret_cast<const float4*>(p.src + pix * p.cs + c4 * 4));
+                        float4 x = __ldg(reinterpret_cast<const float4*>(p.src + pix * p.cs + c4 * 4));
+                        if (pro) {
+                            x.x = fmaf(x.x, sc.x, sf.x);
+                            x.y = fmaf(x.y, sc.y, sf.y);
+                            x.z = fmaf(x.z, sc.z, sf.z);
+                            x.w = fmaf(x.w, sc.w, sf.w);
+                            if (p.pro_relu) {
+                                x.x = fmaxf(x.x, 0.f);
+                                x.y = fmaxf(x.y, 0.f);
+                                x.z = fmaxf(x.z, 0.f);
+                                x.w = fmaxf(x.w, 0.f);
+                            }
+                        }
+                        xa[i] = x;
                     }
                     const float* zrow = p.dz + (size_t)m * p.cd + n_off;
-#pragma unroll
-                    for (int jj = 0; jj < 2; ++jj) {
-                        const int n4 = lane + 32 * jj;
-                        if (n4 * 4 < p.bnt && n_off + n4 * 4 < p.cd)
-                            xb[j][jj] = __ldg(reinterpret_cast<const float4*>(zrow + n4 * 4));
+                    if (cg < nb_blocks && n_off + cg * 4 < p.cd) xb0[i] = __ldg(reinterpret_cast<const float4*>(zrow + cg * 4));
+                    if (cg + 32 < nb_blocks && n_off + (cg + 32) * 4 < p.cd)
+                        xb1[i] = __ldg(reinterpret_cast<const float4*>(zrow + (cg + 32) * 4));
+                    // next pixel
+                    if (++w_ == p.wd) {
+                        w_ = 0;
+                        if (++h_ == p.hd) {
+                            h_ = 0;
+                            if (++t_ == p.td) {
+                                t_ = 0;
+                                ++n_;
+                            }
+                        }
                     }
                 }
-                oka[j] = ok;
             }
+            transpose4(xa);
+            transpose4(xb0);
+            transpose4(xb1);
             sv::mbar_wait(&empty_bar[stage], phase ^ 1);
             const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
             const uint32_t a_lo = a_hi + WG_A_BYTES;
             const uint32_t b_hi = a_lo + WG_A_BYTES;
             const uint32_t b_lo = b_hi + b_bytes;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int pr = prow + 8 * j;     // pixel row in the stage, k-group = j, row in atom = prow
-                float4 x = xa[j];
-                if (pro && oka[j]) {
-                    x.x = fmaf(x.x, sc.x, sf.x);
-                    x.y = fmaf(x.y, sc.y, sf.y);
-                    x.z = fmaf(x.z, sc.z, sf.z);
-                    x.w = fmaf(x.w, sc.w, sf.w);
-                    if (p.pro_relu) {
-                        x.x = fmaxf(x.x, 0.f);
-                        x.y = fmaxf(x.y, 0.f);
-                        x.z = fmaxf(x.z, 0.f);
-                        x.w = fmaxf(x.w, 0.f);
-                    }
-                }
-                {
-                    const uint32_t off = (uint32_t)(((pr >> 3) * 4 + (lane >> 3)) * 1024 + (pr & 7) * 128 +
-                                                    (((lane & 7) ^ (pr & 7)) << 4));
-                    const uint32_t h0 = wg_hi(x.x), h1 = wg_hi(x.y), h2 = wg_hi(x.z), h3 = wg_hi(x.w);
-                    wg_st4(a_hi + off, h0, h1, h2, h3);
-                    if (p.passes == 3)
-                        wg_st4(a_lo + off, __float_as_uint(x.x - __uint_as_float(h0)), __float_as_uint(x.y - __uint_as_float(h1)),
-                               __float_as_uint(x.z - __uint_as_float(h2)), __float_as_uint(x.w - __uint_as_float(h3)));
-                }
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    const int n4 = lane + 32 * jj;
-                    if (n4 < p.natom * 8) {
-                        const float4 z = xb[j][jj];
-                        const uint32_t off = (uint32_t)(((pr >> 3) * p.natom + (n4 >> 3)) * 1024 + (pr & 7) * 128 +
-                                                        (((n4 & 7) ^ (pr & 7)) << 4));
-                        const uint32_t h0 = wg_hi(z.x), h1 = wg_hi(z.y), h2 = wg_hi(z.z), h3 = wg_hi(z.w);
-                        wg_st4(b_hi + off, h0, h1, h2, h3);
-                        if (p.passes == 3)
-                            wg_st4(b_lo + off, __float_as_uint(z.x - __uint_as_float(h0)), __float_as_uint(z.y - __uint_as_float(h1)),
-                                   __float_as_uint(z.z - __uint_as_float(h2)), __float_as_uint(z.w - __uint_as_float(h3)));
-                    }
-                }
-            }
+            const bool with_lo = p.passes == 3;
+            store_rows4(a_hi, a_lo, cg * 4, pg, xa, with_lo);
+            if (cg < nb_blocks) store_rows4(b_hi, b_lo, cg * 4, pg, xb0, with_lo);
+            if (cg + 32 < nb_blocks) store_rows4(b_hi, b_lo, (cg + 32) * 4, pg, xb1, with_lo);
             sv::fence_proxy_async();
             __syncwarp();
             if (lane == 0) sv::mbar_arrive(&full_bar[stage]);
@@ -213,10 +229,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams 
         sv::tc_fence_before();
     } else {
         if (lane == 0) {
-            const uint32_t idesc = sv::make_idesc_tf32(128, p.bnt, 1, 1);  // both operands MN-major
+            const uint32_t idesc = sv::make_idesc_tf32(128, p.bnt, 0, 0);  // both operands K-major (K = pixels)
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t b_sbo = (uint32_t)(p.natom * 1024);
             for (int i = 0; i < nks; ++i) {
                 sv::mbar_wait(&full_bar[stage], phase);
                 sv::tc_fence_after();
@@ -225,17 +240,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams 
                 const uint32_t b_hi = a_lo + WG_A_BYTES;
                 const uint32_t b_lo = b_hi + b_bytes;
 #pragma unroll
-                for (int kg = 0; kg < 4; ++kg) {
-                    const uint64_t da_hi = sv::make_smem_desc(a_hi + kg * 4096, 1024, 4096, 2);
-                    const uint64_t db_hi = sv::make_smem_desc(b_hi + kg * b_sbo, 1024, b_sbo, 2);
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const uint64_t da_hi = sv::make_smem_desc_sw128(a_hi + k4 * 32, 16, 1024);
+                    const uint64_t db_hi = sv::make_smem_desc_sw128(b_hi + k4 * 32, 16, 1024);
                     if (p.passes == 3) {
-                        const uint64_t da_lo = sv::make_smem_desc(a_lo + kg * 4096, 1024, 4096, 2);
-                        const uint64_t db_lo = sv::make_smem_desc(b_lo + kg * b_sbo, 1024, b_sbo, 2);
-                        sv::umma_tf32(tmem_base, da_lo, db_hi, idesc, (i | kg) ? 1u : 0u);
+                        const uint64_t da_lo = sv::make_smem_desc_sw128(a_lo + k4 * 32, 16, 1024);
+                        const uint64_t db_lo = sv::make_smem_desc_sw128(b_lo + k4 * 32, 16, 1024);
+                        sv::umma_tf32(tmem_base, da_lo, db_hi, idesc, (i | k4) ? 1u : 0u);
                         sv::umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
                         sv::umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
                     } else {
-                        sv::umma_tf32(tmem_base, da_hi, db_hi, idesc, (i | kg) ? 1u : 0u);
+                        sv::umma_tf32(tmem_base, da_hi, db_hi, idesc, (i | k4) ? 1u : 0u);
                     }
                 }
                 sv::umma_commit(&empty_bar[stage]);
@@ -339,7 +354,7 @@ extern "C" int selavi_conv_wgrad(const float* src, const float* dz, float* dW, c
     uint32_t cols = 32;
     while ((int)cols < p.bnt) cols <<= 1;
     p.tmem_cols = cols;
-    const int stage_bytes = 2 * WG_A_BYTES + 2 * 4 * p.natom * 1024;
+    const int stage_bytes = 2 * WG_A_BYTES + 2 * p.bnt * 128;
     const int tail_bytes = 8 * 8 * 2 + 8 + 8 + 64;
     int stages = (227 * 1024 - 1024 - tail_bytes) / stage_bytes;
     if (stages > 6) stages = 6;

@@ -1,0 +1,108 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution kernels (forward, data gradient, weight gradient)
+against torch's float64 convolution on the same inputs (a floating-point kernel: torch reference, tolerance
+stated per test).  Shapes are the layer shapes of R(2+1)D-18 / ResNet-9, reduced batch."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# name: (nb, ci, co, (T,H,W), kernel, stride, padding)
+LAYERS = {
+    "gemm_1x1x1": (2, 64, 64, (2, 8, 8), (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+    "v_stem0_7x7": (1, 3, 45, (4, 32, 32), (1, 7, 7), (1, 2, 2), (0, 3, 3)),
+    "v_stem3_t": (1, 45, 64, (4, 16, 16), (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+    "v_l1_spatial": (1, 64, 144, (4, 28, 28), (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    "v_l1_temporal": (1, 144, 64, (4, 14, 14), (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+    "v_l2_spatial_s2": (1, 64, 230, (4, 28, 28), (1, 3, 3), (1, 2, 2), (0, 1, 1)),
+    "v_l2_temporal_s2": (1, 230, 128, (8, 14, 14), (3, 1, 1), (2, 1, 1), (1, 0, 0)),
+    "v_l2_downsample": (1, 64, 128, (8, 28, 28), (1, 1, 1), (2, 2, 2), (0, 0, 0)),
+    "v_l3_spatial_288": (1, 128, 288, (2, 14, 14), (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    "v_l4_spatial_921": (2, 256, 921, (2, 14, 14), (1, 3, 3), (1, 2, 2), (0, 1, 1)),
+    "v_l4_temporal_1152": (2, 1152, 512, (4, 7, 7), (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+    "a_conv1_7x7": (2, 1, 64, (1, 65, 50), (1, 7, 7), (1, 2, 2), (0, 3, 3)),
+    "a_l2_3x3_s2": (2, 64, 128, (1, 33, 25), (1, 3, 3), (1, 2, 2), (0, 1, 1)),
+    "ragged_m": (1, 12, 20, (3, 5, 7), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+}
+
+
+def _mk(name, device):
+    from selavi_b200 import ops
+    nb, ci, co, thw, k, s, p = LAYERS[name]
+    g = torch.Generator(device=device).manual_seed(hash(name) % 1000)
+    x = torch.randn(nb, ci, *thw, device=device, generator=g)
+    w = torch.randn(co, ci, *k, device=device, generator=g) * (1.0 / (ci * k[0] * k[1] * k[2]) ** 0.5)
+    geom = ops.ConvGeom(nb, ci, co, thw, k, s, p)
+    return x, w, geom, (s, p)
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+@pytest.mark.parametrize("name", sorted(LAYERS))
+# passes=3 (tf32x3): operand error ~2^-21; the tensor core adds each K=8 partial product into the fp32
+# accumulator with truncation, so the error grows ~n_mma * 2^-25 (measured 8e-7 at K=64, 4e-6 at K=576).
+@pytest.mark.parametrize("passes,tol", [(3, 5e-5), (1, 2e-3)])
+def test_conv_forward(cuda_device, name, passes, tol):
+    from selavi_b200 import ops
+    x, w, geom, (s, p) = _mk(name, cuda_device)
+    ref = F.conv3d(x.double(), w.double(), None, s, p)
+    y = ops.conv_forward(ops.to_channels_last(x), ops.pack_weights(w, geom, 0), geom, passes=passes)
+    assert y[..., geom.co:].abs().max().item() == 0 if geom.cos > geom.co else True
+    err = _rel(ops.from_channels_last(y, geom.co), ref)
+    print(f"{name} fwd passes={passes} rel={err:.3e}")
+    assert err < tol
+
+
+@pytest.mark.parametrize("name", ["v_l1_spatial", "v_stem3_t", "a_l2_3x3_s2", "ragged_m"])
+def test_conv_forward_fused_bn_relu_prologue_and_stats(cuda_device, name):
+    """prologue = train-mode BN(+ReLU) of the previous layer applied on the fly; epilogue = per-channel stats."""
+    from selavi_b200 import ops
+    x, w, geom, (s, p) = _mk(name, cuda_device)
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    scale = torch.rand(geom.cis, device=cuda_device, generator=g) + 0.5
+    shift = torch.randn(geom.cis, device=cuda_device, generator=g) * 0.3
+    xn = torch.relu(x.double() * scale[:geom.ci].double().view(1, -1, 1, 1, 1) + shift[:geom.ci].double().view(1, -1, 1, 1, 1))
+    ref = F.conv3d(xn, w.double(), None, s, p)
+    stats = ops.stats_buffer(geom, cuda_device)
+    y = ops.conv_forward(ops.to_channels_last(x), ops.pack_weights(w, geom, 0), geom, scale=scale, shift=shift, relu=True,
+                         stats=stats)
+    assert _rel(ops.from_channels_last(y, geom.co), ref) < 5e-5
+    tot = stats.double().sum(0)[:, :geom.co]
+    # fp32 per-tile partial sums: tolerance relative to the L1 / L2 mass of the channel
+    l1 = ref.abs().sum((0, 2, 3, 4))
+    assert float(((tot[0] - ref.sum((0, 2, 3, 4))).abs() / l1).max()) < 1e-5
+    assert float(((tot[1] - (ref * ref).sum((0, 2, 3, 4))).abs() / (ref * ref).sum((0, 2, 3, 4))).max()) < 1e-4
+
+
+@pytest.mark.parametrize("name", sorted(LAYERS))
+def test_conv_dgrad(cuda_device, name):
+    from selavi_b200 import ops
+    x, w, geom, (s, p) = _mk(name, cuda_device)
+    xd = x.double().requires_grad_(True)
+    ref_y = F.conv3d(xd, w.double(), None, s, p)
+    dz = torch.randn(ref_y.shape, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(7))
+    ref_dx, = torch.autograd.grad(ref_y, xd, dz.double())
+    dx = ops.conv_dgrad(ops.to_channels_last(dz), ops.pack_weights(w, geom, 1), geom)
+    err = _rel(ops.from_channels_last(dx, geom.ci), ref_dx)
+    print(f"{name} dgrad rel={err:.3e}")
+    assert err < 5e-5
+    # accumulate=True adds onto the existing gradient (residual joins)
+    dx2 = ops.conv_dgrad(ops.to_channels_last(dz), ops.pack_weights(w, geom, 1), geom, out=dx.clone(), accumulate=True)
+    assert _rel(dx2, 2 * dx) < 1e-6
+
+
+@pytest.mark.parametrize("name", sorted(LAYERS))
+def test_conv_wgrad(cuda_device, name):
+    from selavi_b200 import ops
+    x, w, geom, (s, p) = _mk(name, cuda_device)
+    wd = w.double().requires_grad_(True)
+    ref_y = F.conv3d(x.double(), wd, None, s, p)
+    dz = torch.randn(ref_y.shape, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(9))
+    ref_dw, = torch.autograd.grad(ref_y, wd, dz.double())
+    dw = torch.empty_like(w)
+    ops.conv_wgrad(ops.to_channels_last(x), ops.to_channels_last(dz), geom, dw)
+    err = _rel(dw, ref_dw)
+    print(f"{name} wgrad rel={err:.3e}")
+    assert err < 5e-5

@@ -1,0 +1,34 @@
+"""Run each GPU check in its own subprocess under a timeout (a hung kernel must not take the box down) and
+print one line per check.  Usage on the GPU box:  python tools/gpu_diag.py [pattern]"""
+import subprocess
+import sys
+import time
+
+CHECKS = [
+    ("sk_small", "tests/test_sk_gpu.py::test_sk_matches_oracle"),
+    ("sk_golden", "tests/test_sk_gpu.py::test_sk_matches_reference_golden"),
+    ("sk_cont", "tests/test_sk_gpu.py::test_sk_fixed_iterations_and_continuation"),
+    ("sk_full", "tests/test_sk_gpu.py::test_sk_full_size_properties"),
+    ("conv_fwd_all", "tests/test_conv_gpu.py::test_conv_forward"),
+    ("conv_fwd_pro", "tests/test_conv_gpu.py::test_conv_forward_fused_bn_relu_prologue_and_stats"),
+    ("conv_dgrad", "tests/test_conv_gpu.py::test_conv_dgrad"),
+    ("conv_wgrad_gemm", "tests/test_conv_gpu.py::test_conv_wgrad[gemm_1x1x1]"),
+    ("conv_wgrad", "tests/test_conv_gpu.py::test_conv_wgrad"),
+]
+
+if __name__ == "__main__":
+    pat = sys.argv[1] if len(sys.argv) > 1 else ""
+    for name, target in CHECKS:
+        if pat and pat not in name:
+            continue
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, "-m", "pytest", target, "-q", "-s", "--no-header", "-p", "no:cacheprovider"],
+                               capture_output=True, text=True, timeout=240)
+            lines = (r.stdout + r.stderr).strip().splitlines()
+            keep = [l for l in lines if ("rel=" in l and "print" not in l) or l.startswith("FAILED") or l.startswith("E  ")]
+            tail = "\n".join(keep[:60] + lines[-2:])
+            status = "PASS" if r.returncode == 0 else f"FAIL({r.returncode})"
+        except subprocess.TimeoutExpired as e:
+            status, tail = "TIMEOUT", ((e.stdout or b"").decode(errors="replace")[-2000:] if isinstance(e.stdout, bytes) else str(e.stdout)[-2000:])
+        print(f"==== {name}: {status} in {time.time() - t0:.1f}s\n{tail}\n", flush=True)
