@@ -1,0 +1,584 @@
+"""Execution engine of the B200-native SeLaVi hot path: runs the towers / heads / loss of `model.py` through
+the C-ABI kernels and wires them into torch.autograd (so DDP's gradient hooks, torch optimizers and the
+reference training loop main.py:263-302 work unchanged).
+
+Data layout in HBM: activations channels-last fp32 [N,T,H,W,Cs] (Cs = channels padded to 4).  Every convolution
+stores only its RAW output z; the following train-mode BatchNorm(+ReLU) lives as a per-channel (scale, shift)
+pair that the NEXT convolution applies on the fly in its operand loader ("pending" activation), so normalised
+activations are written to HBM only at residual joins (block outputs), after the stem and after the max-pool.
+BN batch statistics come from the conv epilogue (per-tile partial sums), reduced in fp64.
+
+No torch convolution / batch-norm / linear / cross-entropy call is made anywhere on this path, and there is no
+CPU fallback: tensors must be CUDA and the shared library must be present.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import _lib, ops
+
+# tf32x3 split (fp32-class accuracy) is the parity mode; SELAVI_MMA_PASSES=1 selects single-pass tf32 (fast mode).
+PASSES = int(os.environ.get("SELAVI_MMA_PASSES", "3"))
+
+
+def _stream():
+    return _lib.stream_ptr()
+
+
+def _world(bn):
+    """SyncBatchNorm semantics only when the module was converted (main.py:117-118) and a group is up."""
+    if isinstance(bn, nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(bn.process_group) if bn.process_group is not None else dist.get_world_size()
+    return 1
+
+
+def _allreduce(t, bn):
+    dist.all_reduce(t, group=bn.process_group)
+
+
+class Act:
+    """An activation: a materialised tensor, or a raw conv output with a pending per-channel affine (+ReLU)."""
+    __slots__ = ("t", "scale", "shift", "relu", "c")
+
+    def __init__(self, t, c, scale=None, shift=None, relu=False):
+        self.t, self.c, self.scale, self.shift, self.relu = t, c, scale, shift, relu
+
+
+class ConvRec:
+    """Everything the backward pass needs about one conv+BN unit."""
+    __slots__ = ("conv", "bn", "geom", "inp", "z", "scale", "shift", "mean", "invstd", "count")
+
+
+_pack_cache = {}
+
+
+def _packed(weight, geom, mode):
+    key = (weight.data_ptr(), mode, geom.ci, geom.co, geom.taps)
+    ver = weight._version
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    buf = ops.pack_weights(weight, geom, mode, out=hit[1] if hit is not None else None)
+    _pack_cache[key] = (ver, buf)
+    return buf
+
+
+def _geom_of(conv, nb, thw):
+    if isinstance(conv, nn.Conv3d):
+        k, s, p = conv.kernel_size, conv.stride, conv.padding
+    else:
+        k, s, p = (1,) + tuple(conv.kernel_size), (1,) + tuple(conv.stride), (0,) + tuple(conv.padding)
+    return ops.ConvGeom(nb, conv.in_channels, conv.out_channels, thw, k, s, p)
+
+
+class TowerRunner:
+    """Forward / backward of one encoder tower (video R(2+1)D-18 or audio ResNet) on the C-ABI kernels."""
+
+    def __init__(self, net, kind):
+        self.kind = kind
+
+    # ------------------------------------------------------------------ forward pieces
+    def conv_bn(self, act, conv, bn, training, tape):
+        lib = _lib.lib()
+        x = act.t
+        nb, t, h, w, _ = x.shape
+        geom = _geom_of(conv, nb, (t, h, w))
+        wp = _packed(conv.weight, geom, 0)
+        dev = x.device
+        cs = geom.cos
+        scale = torch.empty(cs, dtype=torch.float32, device=dev)
+        shift = torch.empty(cs, dtype=torch.float32, device=dev)
+        rec = None
+        if training:
+            stats = ops.stats_buffer(geom, dev)
+            z = ops.conv_forward(x, wp, geom, scale=act.scale, shift=act.shift, relu=act.relu, stats=stats, passes=PASSES)
+            sums = torch.empty(2 * cs, dtype=torch.float64, device=dev)
+            _lib.check(lib.selavi_bn_reduce_partials(_lib.ptr(stats), stats.shape[0], stats.shape[2], cs, _lib.ptr(sums),
+                                                     _stream()), "selavi_bn_reduce_partials")
+            count = float(geom.m_out)
+            world = _world(bn)
+            if world > 1:
+                _allreduce(sums, bn)
+                count *= world
+            mean = torch.empty(cs, dtype=torch.float32, device=dev)
+            invstd = torch.empty(cs, dtype=torch.float32, device=dev)
+            track = bn.track_running_stats and bn.running_mean is not None
+            mom = 0.1 if bn.momentum is None else bn.momentum
+            _lib.check(lib.selavi_bn_finalize(_lib.ptr(sums), count, _lib.ptr(bn.weight), _lib.ptr(bn.bias),
+                                              _lib.ptr(bn.running_mean) if track else None,
+                                              _lib.ptr(bn.running_var) if track else None, mom, bn.eps, geom.co, cs,
+                                              _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(mean), _lib.ptr(invstd),
+                                              1 if track else 0, _stream()), "selavi_bn_finalize")
+            if track:
+                self._nbt.append(bn.num_batches_tracked)
+            if tape is not None:
+                rec = ConvRec()
+                rec.conv, rec.bn, rec.geom, rec.inp, rec.z = conv, bn, geom, act, z
+                rec.scale, rec.shift, rec.mean, rec.invstd, rec.count = scale, shift, mean, invstd, count
+        else:
+            z = ops.conv_forward(x, wp, geom, scale=act.scale, shift=act.shift, relu=act.relu, stats=None, passes=PASSES)
+            _lib.check(lib.selavi_bn_eval_affine(_lib.ptr(bn.weight), _lib.ptr(bn.bias), _lib.ptr(bn.running_mean),
+                                                 _lib.ptr(bn.running_var), bn.eps, geom.co, cs, _lib.ptr(scale),
+                                                 _lib.ptr(shift), _stream()), "selavi_bn_eval_affine")
+        return z, scale, shift, rec, geom
+
+    @staticmethod
+    def bn_apply(z, scale, shift, res=None, rscale=None, rshift=None, relu=True):
+        out = torch.empty_like(z)
+        m = z.numel() // z.shape[-1]
+        _lib.check(_lib.lib().selavi_bn_apply(_lib.ptr(z), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(res), _lib.ptr(rscale),
+                                              _lib.ptr(rshift), 1 if relu else 0, _lib.ptr(out), m, z.shape[-1], _stream()),
+                   "selavi_bn_apply")
+        return out
+
+    def block(self, x_act, main, downsample, training, tape):
+        """main: list of (conv, bn) of the residual branch; downsample: (conv, bn) or None.  Returns block output."""
+        act = x_act
+        recs = []
+        z = scale = shift = None
+        for i, (conv, bn) in enumerate(main):
+            z, scale, shift, rec, geom = self.conv_bn(act, conv, bn, training, tape)
+            recs.append(rec)
+            act = Act(z, geom.co, scale, shift, relu=True)
+        rd = None
+        if downsample is not None:
+            zd, sd, bd, rd, _ = self.conv_bn(x_act, downsample[0], downsample[1], training, tape)
+            y = self.bn_apply(z, scale, shift, res=zd, rscale=sd, rshift=bd, relu=True)
+        else:
+            y = self.bn_apply(z, scale, shift, res=x_act.t, relu=True)
+        if tape is not None:
+            tape.append(("block", recs, rd, x_act, y))
+        return Act(y, act.c)
+
+    def forward(self, net, x, training, tape):
+        lib = _lib.lib()
+        self._nbt = []
+        if not (x.is_cuda and x.dtype == torch.float32):
+            raise ValueError("selavi_b200 towers need float32 CUDA input (no CPU fallback)")
+        x = x.contiguous()
+        if self.kind == "video":
+            nb, c, t, h, w = x.shape
+        else:
+            nb, c, h, w = x.shape
+            t = 1
+        cs = ops.pad4(c)
+        x_cl = torch.empty((nb, t, h, w, cs), dtype=torch.float32, device=x.device)
+        _lib.check(lib.selavi_nchw_to_cl(_lib.ptr(x), _lib.ptr(x_cl), nb, c, t * h * w, cs, _stream()), "selavi_nchw_to_cl")
+        act = Act(x_cl, c)
+        if self.kind == "video":
+            stem = net.stem
+            z0, s0, b0, r0, g0 = self.conv_bn(act, stem[0], stem[1], training, tape)
+            z1, s1, b1, r1, g1 = self.conv_bn(Act(z0, g0.co, s0, b0, True), stem[3], stem[4], training, tape)
+            a = self.bn_apply(z1, s1, b1, relu=True)
+            if tape is not None:
+                tape.append(("vstem", r0, r1))
+            act = Act(a, g1.co)
+            for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
+                for blk in layer:
+                    main = [(blk.conv1[0][0], blk.conv1[0][1]), (blk.conv1[0][3], blk.conv1[1]),
+                            (blk.conv2[0][0], blk.conv2[0][1]), (blk.conv2[0][3], blk.conv2[1])]
+                    ds = (blk.downsample[0], blk.downsample[1]) if blk.downsample is not None else None
+                    act = self.block(act, main, ds, training, tape)
+        else:
+            z0, s0, b0, r0, g0 = self.conv_bn(act, net.conv1, net.bn1, training, tape)
+            ho, wo = (g0.ho + 2 - 3) // 2 + 1, (g0.wo + 2 - 3) // 2 + 1
+            pooled = torch.empty((nb, 1, ho, wo, g0.cos), dtype=torch.float32, device=x.device)
+            _lib.check(lib.selavi_maxpool3x3s2_fwd(_lib.ptr(z0), _lib.ptr(s0), _lib.ptr(b0), _lib.ptr(pooled), nb, g0.ho,
+                                                   g0.wo, g0.cos, _stream()), "selavi_maxpool3x3s2_fwd")
+            if tape is not None:
+                tape.append(("astem", r0, s0, b0))
+            act = Act(pooled, g0.co)
+            for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
+                for blk in layer:
+                    main = [(blk.conv1, blk.bn1), (blk.conv2, blk.bn2)]
+                    ds = (blk.downsample[0], blk.downsample[1]) if blk.downsample is not None else None
+                    act = self.block(act, main, ds, training, tape)
+        y = act.t
+        p = y.shape[1] * y.shape[2] * y.shape[3]
+        feat = torch.empty((nb, act.c), dtype=torch.float32, device=x.device)
+        _lib.check(lib.selavi_avgpool_fwd(_lib.ptr(y), _lib.ptr(feat), nb, p, y.shape[-1], act.c, _stream()), "selavi_avgpool_fwd")
+        if tape is not None:
+            tape.append(("pool", tuple(y.shape), act.c))
+        if self._nbt:
+            torch._foreach_add_(self._nbt, 1)
+        return feat
+
+    # ------------------------------------------------------------------ backward pieces
+    def conv_bn_bwd(self, rec, g, mask_mode, grads, act_mask=None, want_dx=True, dx_out=None, dx_accumulate=False,
+                    gres=None, gres_accumulate=False):
+        """g: gradient wrt the (activated) output of this conv+BN unit.  Returns gradient wrt its input activation."""
+        lib = _lib.lib()
+        geom, z = rec.geom, rec.z
+        dev = z.device
+        cs, M = geom.cos, geom.m_out
+        nblk = lib.selavi_bn_bwd_blocks(M)
+        partial = torch.empty(nblk * 2 * cs, dtype=torch.float32, device=dev)
+        sums = torch.empty(2 * cs, dtype=torch.float64, device=dev)
+        _lib.check(lib.selavi_bn_bwd_reduce(_lib.ptr(g), _lib.ptr(z), _lib.ptr(act_mask), mask_mode, _lib.ptr(rec.scale),
+                                            _lib.ptr(rec.shift), _lib.ptr(rec.mean), _lib.ptr(rec.invstd), M, cs,
+                                            _lib.ptr(partial), _lib.ptr(sums), _stream()), "selavi_bn_bwd_reduce")
+        bn = rec.bn
+        if bn.weight is not None and bn.weight.requires_grad:
+            s32 = sums.view(2, cs)[:, :geom.co].float()
+            grads[bn.bias] = s32[0].contiguous()
+            grads[bn.weight] = s32[1].contiguous()
+        if _world(bn) > 1:
+            sums = sums.clone()
+            _allreduce(sums, bn)
+        dz = torch.empty_like(z)
+        _lib.check(lib.selavi_bn_bwd_apply(_lib.ptr(g), _lib.ptr(z), _lib.ptr(act_mask), mask_mode, _lib.ptr(rec.scale),
+                                           _lib.ptr(rec.shift), _lib.ptr(rec.mean), _lib.ptr(rec.invstd), _lib.ptr(sums),
+                                           rec.count, M, cs, _lib.ptr(dz), _lib.ptr(gres), 1 if gres_accumulate else 0,
+                                           _stream()), "selavi_bn_bwd_apply")
+        conv, inp = rec.conv, rec.inp
+        if conv.weight.requires_grad:
+            dw = torch.empty_like(conv.weight)
+            ops.conv_wgrad(inp.t, dz, geom, dw, scale=inp.scale, shift=inp.shift, relu=inp.relu, passes=PASSES)
+            grads[conv.weight] = dw
+        if not want_dx:
+            return None
+        wpt = _packed(conv.weight, geom, 1)
+        return ops.conv_dgrad(dz, wpt, geom, out=dx_out, accumulate=dx_accumulate, passes=PASSES)
+
+    def backward(self, tape, dfeat, grads):
+        lib = _lib.lib()
+        dfeat = dfeat.contiguous()
+        g = None
+        for entry in reversed(tape):
+            kind = entry[0]
+            if kind == "pool":
+                shape, c = entry[1], entry[2]
+                g = torch.empty(shape, dtype=torch.float32, device=dfeat.device)
+                p = shape[1] * shape[2] * shape[3]
+                _lib.check(lib.selavi_avgpool_bwd(_lib.ptr(dfeat), _lib.ptr(g), shape[0], p, shape[-1], c, _stream()),
+                           "selavi_avgpool_bwd")
+            elif kind == "block":
+                _, recs, rd, x_act, y = entry
+                dx = torch.empty_like(x_act.t)
+                if rd is not None:
+                    self.conv_bn_bwd(rd, g, 1, grads, act_mask=y, dx_out=dx, dx_accumulate=False)
+                    d = self.conv_bn_bwd(recs[-1], g, 1, grads, act_mask=y)
+                else:
+                    d = self.conv_bn_bwd(recs[-1], g, 1, grads, act_mask=y, gres=dx, gres_accumulate=False)
+                for rec in reversed(recs[1:-1]):
+                    d = self.conv_bn_bwd(rec, d, 2, grads)
+                self.conv_bn_bwd(recs[0], d, 2, grads, dx_out=dx, dx_accumulate=True)
+                g = dx
+            elif kind == "vstem":
+                _, r0, r1 = entry
+                d = self.conv_bn_bwd(r1, g, 2, grads)
+                self.conv_bn_bwd(r0, d, 2, grads, want_dx=False)
+                g = None
+            elif kind == "astem":
+                _, r0, s0, b0 = entry
+                z0 = r0.z
+                da = torch.empty_like(z0)
+                _lib.check(lib.selavi_maxpool3x3s2_bwd(_lib.ptr(g), _lib.ptr(z0), _lib.ptr(s0), _lib.ptr(b0), _lib.ptr(da),
+                                                       z0.shape[0], z0.shape[2], z0.shape[3], z0.shape[4], _stream()),
+                           "selavi_maxpool3x3s2_bwd")
+                self.conv_bn_bwd(r0, da, 2, grads, want_dx=False)
+                g = None
+
+
+def _tower_params(net):
+    return [p for p in net.parameters()]
+
+
+class _TowerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner, net, x, *params):
+        tape = []
+        feat = runner.forward(net, x, True, tape)
+        ctx.runner, ctx.tape, ctx.params = runner, tape, params
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        grads = {}
+        ctx.runner.backward(ctx.tape, dfeat, grads)
+        ctx.tape = None
+        return (None, None, None) + tuple(grads.get(p) for p in ctx.params)
+
+
+def tower_forward(net, kind, x):
+    """Forward of `R2Plus1D18` / `AudioResNet` (replaces tv:video/resnet.py:246-260 / tv:resnet.py:266-284)."""
+    runner = net.__dict__.get("_sv_runner")
+    if runner is None:
+        runner = TowerRunner(net, kind)
+        net.__dict__["_sv_runner"] = runner
+    params = _tower_params(net)
+    training = net.training
+    if training and torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        return _TowerFn.apply(runner, net, x, *params)
+    if torch.is_grad_enabled() and not training and any(p.requires_grad for p in params) and x.requires_grad:
+        raise NotImplementedError("gradients through an eval-mode tower are outside the hot path")
+    with torch.no_grad():
+        return runner.forward(net, x, training, None)
+
+
+# ====================================================================================================== heads
+_tbl_cache = {}
+
+
+def _ptr_table(tensors):
+    key = tuple(t.data_ptr() for t in tensors)
+    tbl = _tbl_cache.get(key)
+    if tbl is None:
+        tbl = torch.tensor(list(key), dtype=torch.int64, device=tensors[0].device)
+        if len(_tbl_cache) > 4096:
+            _tbl_cache.clear()
+        _tbl_cache[key] = tbl
+    return tbl
+
+
+def _head_parts(head):
+    """-> (lin1 or None, bn or None, lin2, p_drop)"""
+    if isinstance(head, nn.Linear):
+        return None, None, head, 0.0
+    seq = head.block_forward
+    if head.n_hidden is None:
+        return None, None, seq[2], seq[1].p
+    return seq[2], seq[4], seq[8], seq[1].p
+
+
+def _bgemm(H, M, N, K, A=None, A_tbl=None, a=(0, 0, 0), Amask=None, am_bs=0, B=None, B_tbl=None, b=(0, 0, 0), bias=None,
+           bias_tbl=None, bias_bs=0, C=None, c=(0, 0, 0), accumulate=False):
+    _lib.check(_lib.lib().selavi_bgemm(H, M, N, K, _lib.ptr(A), _lib.ptr(A_tbl), a[0], a[1], a[2], _lib.ptr(Amask), am_bs,
+                                       _lib.ptr(B), _lib.ptr(B_tbl), b[0], b[1], b[2], _lib.ptr(bias), _lib.ptr(bias_tbl),
+                                       bias_bs, _lib.ptr(C), c[0], c[1], c[2], 1 if accumulate else 0, _stream()),
+               "selavi_bgemm")
+
+
+class _HeadsRun:
+    """Batched forward/backward of H structurally identical heads sharing one input [B, F]."""
+
+    def __init__(self, heads, training):
+        self.heads = heads
+        self.H = len(heads)
+        parts = [_head_parts(h) for h in heads]
+        self.lin1 = [p[0] for p in parts]
+        self.bn = [p[1] for p in parts]
+        self.lin2 = [p[2] for p in parts]
+        self.p = parts[0][3]
+        self.mlp = self.lin1[0] is not None
+        self.training = training
+        self.params = []
+        for l1, bn, l2 in zip(self.lin1, self.bn, self.lin2):
+            if l1 is not None:
+                self.params += [l1.weight, bn.weight, bn.bias]
+            self.params += [l2.weight] + ([l2.bias] if l2.bias is not None else [])
+
+    def _mask(self, shape, dev):
+        if not self.training or self.p <= 0.0:
+            return None
+        keep = 1.0 - self.p
+        return torch.empty(shape, dtype=torch.float32, device=dev).bernoulli_(keep).div_(keep)
+
+    def forward(self, x, save):
+        lib = _lib.lib()
+        x = x.contiguous()
+        H, (B, F) = self.H, x.shape
+        dev = x.device
+        K = self.lin2[0].out_features
+        w2 = _ptr_table([l.weight for l in self.lin2])
+        b2 = _ptr_table([l.bias for l in self.lin2]) if self.lin2[0].bias is not None else None
+        logits = torch.empty((H, B, K), dtype=torch.float32, device=dev)
+        m1 = self._mask((H, B, F), dev)
+        st = {"x": x, "m1": m1}
+        if self.mlp:
+            Fh = self.lin1[0].out_features
+            w1 = _ptr_table([l.weight for l in self.lin1])
+            z1 = torch.empty((H, B, Fh), dtype=torch.float32, device=dev)
+            # z1[h] = (x * m1[h]) @ W1[h]^T
+            _bgemm(H, B, Fh, F, A=x, a=(0, F, 1), Amask=m1, am_bs=B * F, B_tbl=w1, b=(0, 1, F), C=z1, c=(B * Fh, Fh, 1))
+            scale = torch.empty((H, Fh), dtype=torch.float32, device=dev)
+            shift = torch.empty_like(scale)
+            gam, bet = _ptr_table([b.weight for b in self.bn]), _ptr_table([b.bias for b in self.bn])
+            rm, rv = _ptr_table([b.running_mean for b in self.bn]), _ptr_table([b.running_var for b in self.bn])
+            bn0 = self.bn[0]
+            if self.training:
+                sums = torch.empty((H, 2, Fh), dtype=torch.float64, device=dev)
+                _lib.check(lib.selavi_heads_bn_stats(_lib.ptr(z1), H, B, Fh, _lib.ptr(sums), _stream()), "selavi_heads_bn_stats")
+                count = float(B)
+                world = _world(bn0)
+                if world > 1:
+                    _allreduce(sums, bn0)
+                    count *= world
+                mean = torch.empty_like(scale)
+                invstd = torch.empty_like(scale)
+                mom = 0.1 if bn0.momentum is None else bn0.momentum
+                _lib.check(lib.selavi_heads_bn_finalize(_lib.ptr(sums), count, _lib.ptr(gam), _lib.ptr(bet), _lib.ptr(rm),
+                                                        _lib.ptr(rv), mom, bn0.eps, H, Fh, _lib.ptr(scale), _lib.ptr(shift),
+                                                        _lib.ptr(mean), _lib.ptr(invstd), 1, _stream()),
+                           "selavi_heads_bn_finalize")
+                torch._foreach_add_([b.num_batches_tracked for b in self.bn], 1)
+                st.update(mean=mean, invstd=invstd, count=count)
+            else:
+                _lib.check(lib.selavi_heads_bn_eval_affine(_lib.ptr(gam), _lib.ptr(bet), _lib.ptr(rm), _lib.ptr(rv), bn0.eps,
+                                                           H, Fh, _lib.ptr(scale), _lib.ptr(shift), _stream()),
+                           "selavi_heads_bn_eval_affine")
+            m2 = self._mask((H, B, Fh), dev)
+            a1 = torch.empty_like(z1)
+            _lib.check(lib.selavi_heads_act(_lib.ptr(z1), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(m2), _lib.ptr(a1), H, B,
+                                            Fh, _stream()), "selavi_heads_act")
+            _bgemm(H, B, K, Fh, A=a1, a=(B * Fh, Fh, 1), B_tbl=w2, b=(0, 1, Fh), bias_tbl=b2, C=logits, c=(B * K, K, 1))
+            st.update(z1=z1, a1=a1, m2=m2, scale=scale, shift=shift, w1=w1)
+        else:
+            _bgemm(H, B, K, F, A=x, a=(0, F, 1), Amask=m1, am_bs=B * F, B_tbl=w2, b=(0, 1, F), bias_tbl=b2, C=logits,
+                   c=(B * K, K, 1))
+        st["w2"] = w2
+        return logits, (st if save else None)
+
+    def backward(self, st, dlogits):
+        """dlogits [H,B,K] contiguous -> (dx [B,F], grads in self.params order)"""
+        lib = _lib.lib()
+        H = self.H
+        x = st["x"]
+        B, F = x.shape
+        dev = x.device
+        K = self.lin2[0].out_features
+        has_bias = self.lin2[0].bias is not None
+        db2 = None
+        if has_bias:
+            db2 = torch.empty((H, K), dtype=torch.float32, device=dev)
+            _lib.check(lib.selavi_heads_colsum(_lib.ptr(dlogits), _lib.ptr(db2), H, B, K, _stream()), "selavi_heads_colsum")
+        dx = torch.empty((B, F), dtype=torch.float32, device=dev)
+        if self.mlp:
+            Fh = self.lin1[0].out_features
+            a1, z1 = st["a1"], st["z1"]
+            # dW2[h] = dlogits[h]^T @ a1[h]      [K, Fh]
+            dW2 = torch.empty((H, K, Fh), dtype=torch.float32, device=dev)
+            _bgemm(H, K, Fh, B, A=dlogits, a=(B * K, 1, K), B=a1, b=(B * Fh, Fh, 1), C=dW2, c=(K * Fh, Fh, 1))
+            # da1[h] = dlogits[h] @ W2[h]        [B, Fh]
+            da1 = torch.empty((H, B, Fh), dtype=torch.float32, device=dev)
+            _bgemm(H, B, Fh, K, A=dlogits, a=(B * K, K, 1), B_tbl=st["w2"], b=(0, Fh, 1), C=da1, c=(B * Fh, Fh, 1))
+            sums = torch.empty((H, 2, Fh), dtype=torch.float64, device=dev)
+            _lib.check(lib.selavi_heads_bn_bwd_reduce(_lib.ptr(da1), _lib.ptr(st["m2"]), _lib.ptr(z1), _lib.ptr(st["scale"]),
+                                                      _lib.ptr(st["shift"]), _lib.ptr(st["mean"]), _lib.ptr(st["invstd"]), H,
+                                                      B, Fh, _lib.ptr(sums), _stream()), "selavi_heads_bn_bwd_reduce")
+            dgamma = sums[:, 1].float()
+            dbeta = sums[:, 0].float()
+            bn0 = self.bn[0]
+            if _world(bn0) > 1:
+                sums = sums.clone()
+                _allreduce(sums, bn0)
+            dz1 = torch.empty_like(z1)
+            _lib.check(lib.selavi_heads_bn_bwd_apply(_lib.ptr(da1), _lib.ptr(st["m2"]), _lib.ptr(z1), _lib.ptr(st["scale"]),
+                                                     _lib.ptr(st["shift"]), _lib.ptr(st["mean"]), _lib.ptr(st["invstd"]),
+                                                     _lib.ptr(sums), st["count"], H, B, Fh, _lib.ptr(dz1), _stream()),
+                       "selavi_heads_bn_bwd_apply")
+            # dW1[h] = dz1[h]^T @ (x * m1[h])    [Fh, F]
+            dW1 = torch.empty((H, Fh, F), dtype=torch.float32, device=dev)
+            if st["m1"] is None:
+                _bgemm(H, Fh, F, B, A=dz1, a=(B * Fh, 1, Fh), B=x, b=(0, F, 1), C=dW1, c=(Fh * F, F, 1))
+            else:
+                self._dw1_masked(dz1, x, st["m1"], dW1, H, B, Fh, F)
+            # dd1[h] = dz1[h] @ W1[h]  [B, F];  dx = sum_h dd1[h] * m1[h]
+            dd1 = torch.empty((H, B, F), dtype=torch.float32, device=dev)
+            _bgemm(H, B, F, Fh, A=dz1, a=(B * Fh, Fh, 1), B_tbl=st["w1"], b=(0, F, 1), C=dd1, c=(B * F, F, 1))
+            _lib.check(lib.selavi_heads_sum_masked(_lib.ptr(dd1), _lib.ptr(st["m1"]), _lib.ptr(dx), H, B * F, 0, _stream()),
+                       "selavi_heads_sum_masked")
+            grads = []
+            for h in range(H):
+                grads += [dW1[h], dgamma[h].contiguous(), dbeta[h].contiguous(), dW2[h]] + ([db2[h]] if has_bias else [])
+        else:
+            dW2 = torch.empty((H, K, F), dtype=torch.float32, device=dev)
+            if st["m1"] is None:
+                _bgemm(H, K, F, B, A=dlogits, a=(B * K, 1, K), B=x, b=(0, F, 1), C=dW2, c=(K * F, F, 1))
+            else:
+                self._dw1_masked(dlogits, x, st["m1"], dW2, H, B, K, F)
+            dd = torch.empty((H, B, F), dtype=torch.float32, device=dev)
+            _bgemm(H, B, F, K, A=dlogits, a=(B * K, K, 1), B_tbl=st["w2"], b=(0, F, 1), C=dd, c=(B * F, F, 1))
+            _lib.check(lib.selavi_heads_sum_masked(_lib.ptr(dd), _lib.ptr(st["m1"]), _lib.ptr(dx), H, B * F, 0, _stream()),
+                       "selavi_heads_sum_masked")
+            grads = []
+            for h in range(H):
+                grads += [dW2[h]] + ([db2[h]] if has_bias else [])
+        return dx, grads
+
+    @staticmethod
+    def _dw1_masked(dz, x, m1, dW, H, B, Fh, F):
+        """dW[h] = dz[h]^T @ (x * m1[h]): the masked operand must be the reduced-over (k = batch row) matrix B(k, n),
+        so swap roles: dW[h]^T = (x*m1[h])^T @ dz[h]  ->  write with transposed C strides."""
+        _bgemm(H, F, Fh, B, A=x, a=(0, 1, F), Amask=m1, am_bs=B * F, B=dz, b=(B * Fh, Fh, 1), C=dW, c=(Fh * F, 1, F))
+
+
+class _HeadsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, run, x, *params):
+        logits, st = run.forward(x, save=True)
+        ctx.run, ctx.st = run, st
+        outs = tuple(logits[h] for h in range(run.H))
+        ctx.shape = tuple(logits.shape)
+        return outs
+
+    @staticmethod
+    def backward(ctx, *douts):
+        run = ctx.run
+        H, B, K = ctx.shape
+        dl = torch.empty((H, B, K), dtype=torch.float32, device=ctx.st["x"].device)
+        for h, d in enumerate(douts):
+            if d is None:
+                dl[h].zero_()
+            else:
+                dl[h].copy_(d)
+        dx, grads = run.backward(ctx.st, dl)
+        ctx.st = None
+        return (None, dx) + tuple(grads)
+
+
+def heads_forward(heads, x):
+    """All heads of one modality in batched launches (replaces the per-head loop model.py:233-252)."""
+    if not (x.is_cuda and x.dtype == torch.float32):
+        raise ValueError("selavi_b200 heads need float32 CUDA input (no CPU fallback)")
+    if x.dim() != 2:
+        x = x.reshape(x.shape[0], -1)
+    run = _HeadsRun(heads, heads[0].training)
+    need = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in run.params))
+    if need:
+        return list(_HeadsFn.apply(run, x, *run.params))
+    with torch.no_grad():
+        logits, _ = run.forward(x, save=False)
+    return [logits[h] for h in range(run.H)]
+
+
+# ====================================================================================================== loss
+class _CEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, targets, H, *logits):
+        lib = _lib.lib()
+        B, K = logits[0].shape
+        dev = logits[0].device
+        logits = [l.contiguous() for l in logits]
+        tbl = torch.tensor([l.data_ptr() for l in logits], dtype=torch.int64, device=dev)
+        targets = targets.to(torch.int64)
+        if H == 1 and targets.dim() == 1:
+            sb, sh = targets.stride(0), 0
+        else:
+            sb, sh = targets.stride(0), targets.stride(1)
+        rows = torch.empty((H, B), dtype=torch.float32, device=dev)
+        mean = torch.empty(1, dtype=torch.float32, device=dev)
+        dl = torch.empty((H, B, K), dtype=torch.float32, device=dev)
+        _lib.check(lib.selavi_ce_loss(_lib.ptr(tbl), _lib.ptr(targets), sb, sh, H, B, K, 1.0 / (H * B), _lib.ptr(rows),
+                                      _lib.ptr(mean), _lib.ptr(dl), _stream()), "selavi_ce_loss")
+        ctx.dl = dl
+        ctx.keep = (logits, tbl, targets)
+        return mean.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        dl = ctx.dl * dloss
+        return (None, None) + tuple(dl[h] for h in range(dl.shape[0]))
+
+
+def get_loss(activations, targets, headcount=1):
+    """utils.py:377-387: mean over heads of cross_entropy(activations[h], targets[:, h])."""
+    if headcount == 1:
+        acts = [activations] if torch.is_tensor(activations) else list(activations)
+    else:
+        acts = list(activations)[:headcount]
+    if not acts[0].is_cuda:
+        raise ValueError("selavi_b200.get_loss needs CUDA logits (no CPU fallback)")
+    return _CEFn.apply(targets, len(acts), *acts)

@@ -1,0 +1,50 @@
+"""Fused multi-tensor SGD (momentum + weight decay) — one kernel launch for all 247 parameter tensors.
+
+Same update rule and constructor as `torch.optim.SGD(params, lr, momentum, weight_decay)` used at
+main.py:132-137 (dampening 0, no nesterov): d = g + wd*p; buf = d on the first step else mu*buf + d; p -= lr*buf.
+`state_dict()` uses torch's layout (`momentum_buffer` per parameter), so checkpoints are interchangeable.
+"""
+import torch
+
+from . import _lib
+
+
+class SGD(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, momentum=0.0, dampening=0, weight_decay=0.0, nesterov=False):
+        if dampening != 0 or nesterov:
+            raise NotImplementedError("selavi_b200.optim.SGD implements the reference's configuration (no dampening/nesterov)")
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay, dampening=0, nesterov=False))
+        self._tables = {}
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _lib.lib()
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            first = False
+            for p in ps:
+                st = self.state[p]
+                if "momentum_buffer" not in st or st["momentum_buffer"] is None:
+                    st["momentum_buffer"] = torch.zeros_like(p)
+                    first = True
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()):
+                    raise ValueError("selavi_b200.optim.SGD needs contiguous fp32 CUDA parameters and gradients")
+            key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["momentum_buffer"].data_ptr()) for p in ps)
+            tbl = self._tables.get(gi)
+            if tbl is None or tbl[0] != key:
+                rows = []
+                for p in ps:
+                    rows += [p.data_ptr(), p.grad.data_ptr(), self.state[p]["momentum_buffer"].data_ptr(), p.numel()]
+                tbl = (key, torch.tensor(rows, dtype=torch.int64, device=ps[0].device))
+                self._tables[gi] = tbl
+            with torch.cuda.device(ps[0].device):
+                _lib.check(lib.selavi_sgd_step(_lib.ptr(tbl[1]), len(ps), float(group["lr"]), float(group["momentum"]),
+                                               float(group["weight_decay"]), 1 if first else 0, _lib.stream_ptr()),
+                           "selavi_sgd_step")
+        return loss

@@ -1,0 +1,98 @@
+"""Generate tests/golden/model_*.npz by running the UNMODIFIED reference model (/root/reference/model.py +
+utils.get_loss) on CPU in fp32 (and an fp64 copy as accuracy arbiter).  Authoring container only:
+    python tests/golden/gen_golden_model.py
+Inputs are regenerated from numpy seeds (see `make_inputs`), weights from torch.manual_seed(31) — selavi_b200's
+model reproduces the reference's initialisation order exactly (tests/test_model_cpu.py), so only outputs are stored.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+# name: (B, T, HW, spec_T, K, headcount)
+CONFIGS = {
+    "cfg1": (2, 8, 112, 99, 28, 1),          # BASELINE.json configs[0]
+    "mini_cfg2": (2, 4, 64, 40, 309, 3),     # multi-head / K=309 shape at reduced size
+}
+SMALL = ("bn", "bias", "mlp_v.block_forward.8", "mlp_a.block_forward.8", "mlp_v0.block_forward.8", "stem.0.weight",
+         "audio_network.base.conv1.weight", "downsample.0.weight")
+
+
+def make_inputs(name):
+    B, T, HW, ST, K, hc = CONFIGS[name]
+    rng = np.random.default_rng(31)
+    video = rng.standard_normal((B, 3, T, HW, HW)).astype(np.float32)
+    spec = (rng.standard_normal((B, 1, 257, ST)) * 17.89 + 1.93).astype(np.float32)
+    labels = rng.integers(0, K, size=(B, hc)).astype(np.int64)
+    return video, spec, labels
+
+
+def build(load_model, name):
+    B, T, HW, ST, K, hc = CONFIGS[name]
+    torch.manual_seed(31)
+    m = load_model(vid_base_arch='r2plus1d_18', aud_base_arch='resnet9', pretrained=False, norm_feat=False, use_mlp=True,
+                   headcount=hc, num_classes=K)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    return m
+
+
+def step(m, get_loss, video, spec, labels, hc, dtype):
+    m = m.to(dtype).train()
+    fv, fa = m(torch.from_numpy(video).to(dtype), torch.from_numpy(spec).to(dtype))
+    lab = torch.from_numpy(labels)
+    lab = lab[:, 0] if hc == 1 else lab
+    loss = 0.5 * get_loss(fv, lab, headcount=hc) + 0.5 * get_loss(fa, lab, headcount=hc)
+    m.zero_grad()
+    loss.backward()
+    lv = torch.stack(list(fv)) if hc > 1 else fv[None]
+    la = torch.stack(list(fa)) if hc > 1 else fa[None]
+    return lv.detach(), la.detach(), loss.detach()
+
+
+def main():
+    from oracle import ref_loader
+    ref = ref_loader.load_model_module()
+    get_loss = ref_loader.load_utils_get_loss()
+    for name, (B, T, HW, ST, K, hc) in CONFIGS.items():
+        video, spec, labels = make_inputs(name)
+        m32 = build(ref.load_model, name)
+        m64 = copy.deepcopy(m32)
+        lv, la, loss = step(m32, get_loss, video, spec, labels, hc, torch.float32)
+        lv64, la64, loss64 = step(m64, get_loss, video, spec, labels, hc, torch.float64)
+        out = {"logits_v": lv.numpy(), "logits_a": la.numpy(), "loss": loss.numpy(), "logits_v64": lv64.numpy(),
+               "logits_a64": la64.numpy(), "loss64": loss64.numpy()}
+        m32.eval()
+        with torch.no_grad():
+            m32.return_features = True
+            fv, fa = m32(torch.from_numpy(video), torch.from_numpy(spec))
+            m32.return_features = False
+        out["eval_feat_v"], out["eval_feat_a"] = fv.numpy(), fa.numpy()
+        names, norms, norms64 = [], [], []
+        p64 = dict(m64.named_parameters())
+        for n, p in m32.named_parameters():
+            names.append(n)
+            norms.append(float(p.grad.norm()))
+            norms64.append(float(p64[n].grad.norm()))
+            if any(s in n for s in SMALL) and p.numel() <= 12000:
+                out["grad/" + n] = p.grad.numpy()
+                out["grad64/" + n] = p64[n].grad.numpy()
+        out["grad_names"] = np.array(names)
+        out["grad_norms"] = np.array(norms)
+        out["grad_norms64"] = np.array(norms64)
+        for n, b in m32.named_buffers():
+            if "running" in n and ("stem.1" in n or "layer4.1.conv2.1" in n or "audio_network.base.bn1" in n or "block_forward.4" in n):
+                out["buf/" + n] = b.numpy()
+        np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), f"model_{name}.npz"), **out)
+        print(name, "loss", float(loss), "loss64", float(loss64), "logit err32 vs 64:",
+              float((lv.double() - lv64).norm() / lv64.norm()), flush=True)
+
+
+if __name__ == "__main__":
+    main()

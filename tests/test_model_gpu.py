@@ -1,0 +1,155 @@
+"""GPU parity of the full model path (towers + heads + loss, forward and backward) against golden vectors produced
+by the UNMODIFIED reference on CPU (tests/golden/model_*.npz, generator tests/golden/gen_golden_model.py).
+Tolerance: BASELINE.json north_star — logits within 1e-3 relative of the reference fp32 logits."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from gen_golden_model import CONFIGS, build, make_inputs  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_train_step_matches_reference(cuda_device, name):
+    from selavi_b200 import model as sv_model
+    from selavi_b200.utils import get_loss
+    B, T, HW, ST, K, hc = CONFIGS[name]
+    gold = np.load(os.path.join(GOLDEN, f"model_{name}.npz"))
+    video, spec, labels = make_inputs(name)
+    m = build(sv_model.load_model, name).to(cuda_device).train()
+    fv, fa = m(torch.from_numpy(video).to(cuda_device), torch.from_numpy(spec).to(cuda_device))
+    lab = torch.from_numpy(labels).to(cuda_device)
+    lab = lab[:, 0] if hc == 1 else lab
+    loss = 0.5 * get_loss(fv, lab, headcount=hc) + 0.5 * get_loss(fa, lab, headcount=hc)
+    m.zero_grad()
+    loss.backward()
+    lv = (torch.stack(list(fv)) if hc > 1 else fv[None]).detach().cpu().numpy()
+    la = (torch.stack(list(fa)) if hc > 1 else fa[None]).detach().cpu().numpy()
+    ev, ea = _rel(lv, gold["logits_v"]), _rel(la, gold["logits_a"])
+    print(f"{name}: logits rel err video {ev:.2e} audio {ea:.2e} (vs fp64: {_rel(lv, gold['logits_v64']):.2e} "
+          f"{_rel(la, gold['logits_a64']):.2e}; reference fp32 vs fp64: {_rel(gold['logits_v'], gold['logits_v64']):.2e})")
+    assert ev < 1e-3 and ea < 1e-3
+    assert np.array_equal(lv.argmax(-1), gold["logits_v"].argmax(-1))        # bit-exact argmax cluster ids
+    assert np.array_equal(la.argmax(-1), gold["logits_a"].argmax(-1))
+    assert abs(float(loss) - float(gold["loss"])) < 1e-4 * abs(float(gold["loss"]))
+    # gradients: every parameter's norm, and full tensors for a sample of small parameters
+    grads = {n: p.grad for n, p in m.named_parameters()}
+    worst = 0.0
+    for n, ref_norm, ref_norm64 in zip(gold["grad_names"], gold["grad_norms"], gold["grad_norms64"]):
+        g = grads[str(n)]
+        assert g is not None, n
+        e = abs(float(g.norm()) - ref_norm64) / max(ref_norm64, 1e-12)
+        worst = max(worst, e)
+        assert e < 5e-3, (n, float(g.norm()), ref_norm, ref_norm64)
+    worst_t = 0.0
+    for key in gold.files:
+        if key.startswith("grad64/"):
+            n = key[len("grad64/"):]
+            e = _rel(grads[n].detach().cpu().numpy(), gold[key])
+            worst_t = max(worst_t, e)
+            assert e < 5e-3, (n, e, _rel(gold["grad/" + n], gold[key]))
+    print(f"{name}: worst grad-norm err {worst:.2e}, worst grad-tensor err {worst_t:.2e}")
+    sd = m.state_dict()
+    for key in gold.files:
+        if key.startswith("buf/"):
+            assert _rel(sd[key[4:]].cpu().numpy(), gold[key]) < 1e-4, key
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_eval_features_match_reference(cuda_device, name):
+    """eval-mode (running-stat BN) 512-d features as used by the SK feature sweep (src/sk_utils.py:185-211); the
+    train step of the golden run is replayed first so the running statistics are the same."""
+    from selavi_b200 import model as sv_model
+    B, T, HW, ST, K, hc = CONFIGS[name]
+    gold = np.load(os.path.join(GOLDEN, f"model_{name}.npz"))
+    video, spec, labels = make_inputs(name)
+    m = build(sv_model.load_model, name).to(cuda_device).train()
+    v, s = torch.from_numpy(video).to(cuda_device), torch.from_numpy(spec).to(cuda_device)
+    with torch.no_grad():
+        m(v, s)
+        m.eval()
+        m.return_features = True
+        fv, fa = m(v, s)
+    assert tuple(fv.shape) == (B, 512) and tuple(fa.shape) == (B, 512)
+    ev, ea = _rel(fv.cpu().numpy(), gold["eval_feat_v"]), _rel(fa.cpu().numpy(), gold["eval_feat_a"])
+    print(f"{name}: eval feature rel err video {ev:.2e} audio {ea:.2e}")
+    assert ev < 1e-3 and ea < 1e-3
+
+
+def test_sgd_matches_torch(cuda_device):
+    from selavi_b200.optim import SGD
+    g = torch.Generator(device=cuda_device).manual_seed(1)
+    ps = [torch.randn(n, device=cuda_device, generator=g) for n in (5, 1000, 70001)]
+    a = [torch.nn.Parameter(p.clone()) for p in ps]
+    b = [torch.nn.Parameter(p.clone()) for p in ps]
+    oa = SGD(a, lr=0.05, momentum=0.9, weight_decay=1e-4)
+    ob = torch.optim.SGD(b, lr=0.05, momentum=0.9, weight_decay=1e-4)
+    for _ in range(3):
+        for x, y in zip(a, b):
+            gr = torch.randn(x.shape, device=cuda_device, generator=g)
+            x.grad, y.grad = gr.clone(), gr.clone()
+        oa.step()
+        ob.step()
+    for x, y in zip(a, b):
+        torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-7)
+
+
+def test_heads_linear_and_dropout_paths(cuda_device):
+    """use_mlp=False heads and train-mode dropout masks: gradients checked against torch autograd on the same masks."""
+    from selavi_b200 import engine, model as sv_model
+    torch.manual_seed(3)
+    heads = [sv_model.MLPv2(512, 28).to(cuda_device).train() for _ in range(3)]
+    x = torch.randn(6, 512, device=cuda_device, requires_grad=True)
+    run = engine._HeadsRun(heads, True)
+    logits, st = run.forward(x.detach(), save=True)
+    dl = torch.randn_like(logits)
+    dx, grads = run.backward(st, dl)
+    # torch reference with the same masks
+    xr = x.detach().double().requires_grad_(True)
+    tot = 0
+    for h, head in enumerate(heads):
+        seq = head.block_forward
+        w1, w2, b2 = seq[2].weight.double(), seq[8].weight.double(), seq[8].bias.double()
+        z1 = (xr * st["m1"][h].double()) @ w1.t()
+        mu, var = z1.mean(0), z1.var(0, unbiased=False)
+        y1 = (z1 - mu) / torch.sqrt(var + 1e-5) * seq[4].weight.double() + seq[4].bias.double()
+        a1 = torch.relu(y1) * st["m2"][h].double()
+        lg = a1 @ w2.t() + b2
+        torch.testing.assert_close(logits[h].double(), lg, rtol=1e-4, atol=1e-4)
+        tot = tot + (lg * dl[h].double()).sum()
+    ref_dx, = torch.autograd.grad(tot, xr)
+    torch.testing.assert_close(dx.double(), ref_dx, rtol=1e-3, atol=1e-4)
+    lin = [sv_model.LinearHead(512, 16).to(cuda_device) for _ in range(2)]
+    outs = engine.heads_forward(lin, x)
+    for o, l in zip(outs, lin):
+        torch.testing.assert_close(o, torch.nn.functional.linear(x, l.weight, l.bias), rtol=1e-4, atol=1e-4)
+    sum(o.sum() for o in outs).backward()
+    assert x.grad is not None and lin[0].weight.grad is not None
+
+
+def test_ce_loss_matches_torch(cuda_device):
+    from selavi_b200.utils import get_loss
+    g = torch.Generator(device=cuda_device).manual_seed(2)
+    acts = [torch.randn(16, 309, device=cuda_device, generator=g, requires_grad=True) for _ in range(10)]
+    tg = torch.randint(0, 309, (16, 10), device=cuda_device, generator=g)
+    loss = get_loss(acts, tg, headcount=10)
+    ref = torch.stack([torch.nn.functional.cross_entropy(a.detach().double(), tg[:, h]) for h, a in enumerate(acts)]).mean()
+    assert abs(float(loss) - float(ref)) < 1e-5
+    (loss * 2).backward()
+    a0 = acts[3].detach().double().requires_grad_(True)
+    (torch.nn.functional.cross_entropy(a0, tg[:, 3]) / 10 * 2).backward()
+    torch.testing.assert_close(acts[3].grad.double(), a0.grad, rtol=1e-4, atol=1e-7)
+    one = torch.randn(16, 28, device=cuda_device, requires_grad=True)
+    t1 = torch.randint(0, 28, (16,), device=cuda_device)
+    assert abs(float(get_loss(one, t1)) - float(torch.nn.functional.cross_entropy(one.detach(), t1))) < 1e-5

@@ -35,3 +35,30 @@ def test_oracle_invariants():
     P = (PS ** 10) * out["beta"][:, None] * out["alpha"][None, :]
     np.testing.assert_allclose(P.sum(1), 1.0 / 600, rtol=1e-9)
     np.testing.assert_allclose(P.sum(0), 1.0 / 28, rtol=1e-6)
+
+
+def test_model_oracle_matches_reference_golden():
+    """oracle/model_oracle.py (torchvision/torch.nn restatement of model.py + get_loss) reproduces the golden
+    outputs of the real reference (tests/golden/model_cfg1.npz) bit for bit."""
+    import torch
+    from gen_golden_model import CONFIGS, make_inputs
+    from oracle.model_oracle import OracleAVModel, oracle_get_loss
+    name = "cfg1"
+    B, T, HW, ST, K, hc = CONFIGS[name]
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"model_{name}.npz"))
+    video, spec, labels = make_inputs(name)
+    torch.manual_seed(31)
+    m = OracleAVModel(hc, K)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    m.train()
+    fv, fa = m(torch.from_numpy(video), torch.from_numpy(spec))
+    lab = torch.from_numpy(labels)[:, 0]
+    loss = 0.5 * oracle_get_loss(fv, lab) + 0.5 * oracle_get_loss(fa, lab)
+    loss.backward()
+    assert np.array_equal(fv.detach().numpy()[None], gold["logits_v"])
+    assert np.array_equal(fa.detach().numpy()[None], gold["logits_a"])
+    assert float(loss) == float(gold["loss"])
+    norms = np.array([float(p.grad.norm()) for _, p in m.named_parameters()])
+    np.testing.assert_allclose(norms, gold["grad_norms"], rtol=1e-6)

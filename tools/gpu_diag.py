@@ -14,19 +14,24 @@ CHECKS = [
     ("conv_dgrad", "tests/test_conv_gpu.py::test_conv_dgrad"),
     ("conv_wgrad_gemm", "tests/test_conv_gpu.py::test_conv_wgrad[gemm_1x1x1]"),
     ("conv_wgrad", "tests/test_conv_gpu.py::test_conv_wgrad"),
+    ("heads", "tests/test_model_gpu.py::test_heads_linear_and_dropout_paths"),
+    ("ce", "tests/test_model_gpu.py::test_ce_loss_matches_torch"),
+    ("sgd", "tests/test_model_gpu.py::test_sgd_matches_torch"),
+    ("model_train", "tests/test_model_gpu.py::test_train_step_matches_reference"),
+    ("model_eval", "tests/test_model_gpu.py::test_eval_features_match_reference"),
 ]
 
 if __name__ == "__main__":
-    pat = sys.argv[1] if len(sys.argv) > 1 else ""
+    pats = sys.argv[1:]
     for name, target in CHECKS:
-        if pat and pat not in name:
+        if pats and not any(p in name for p in pats):
             continue
         t0 = time.time()
         try:
             r = subprocess.run([sys.executable, "-m", "pytest", target, "-q", "-s", "--no-header", "-p", "no:cacheprovider"],
                                capture_output=True, text=True, timeout=240)
             lines = (r.stdout + r.stderr).strip().splitlines()
-            keep = [l for l in lines if ("rel=" in l and "print" not in l) or l.startswith("FAILED") or l.startswith("E  ")]
+            keep = [l for l in lines if (("rel=" in l or "rel err" in l or "worst" in l) and "print" not in l) or l.startswith("FAILED") or l.startswith("E  ")]
             tail = "\n".join(keep[:60] + lines[-2:])
             status = "PASS" if r.returncode == 0 else f"FAIL({r.returncode})"
         except subprocess.TimeoutExpired as e:
