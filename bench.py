@@ -1,0 +1,304 @@
+"""Benchmark of the SeLaVi data-parallel training hot path on B200 (contract: see the task statement / DESIGN.md §6).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun launches it for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+A step = one train step of BASELINE.json configs[1] (per-GPU batch 16 synthetic clips 3x32x112x112 + spectrograms
+1x257x200, K=309, 10 heads): forward of both towers and the heads, 0.5*CE_v + 0.5*CE_a, zero_grad, backward
+(DDP gradient all-reduce + SyncBN statistics for N > 1) and the SGD update.  `value` times it with the batch
+resident in HBM; `e2e` repeats it through the public API from pinned host buffers (H2D of the batch and D2H of
+the loss inside the timed region).  The Sinkhorn-Knopp assignment is timed separately (`sk`): cfg-5's matrix
+(N=200000 x K=309 float64, rows sharded over the ranks), exactly 100 iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "clips/sec (video+audio fwd/bwd + SK assign)"
+CFG = dict(batch=16, T=32, HW=112, spec_T=200, K=309, hc=10)
+# SURVEY §8d / BASELINE.md §3: algorithmic conv+linear FLOPs of one train step per sample (3x fwd - input dgrads)
+FLOP_PER_SAMPLE_STEP = 490.3e9
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return dict(hbm=p["hbm_gbs"], tensor=p.get("bf16_tflops_sustained", p["bf16_tflops"]), src="measured")
+    except Exception:  # noqa: BLE001
+        return dict(hbm=6650.0, tensor=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        if not rows:
+            return None
+        sm = sorted(int(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+
+def synthetic_batch(torch, rank, batch):
+    g = torch.Generator().manual_seed(31 + rank)
+    video = torch.randn(batch, 3, CFG["T"], CFG["HW"], CFG["HW"], generator=g)
+    spec = torch.randn(batch, 1, 257, CFG["spec_T"], generator=g) * 17.89 + 1.93
+    labels = torch.randint(0, CFG["K"], (batch, CFG["hc"]), generator=g)
+    return video, spec, labels
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_train_throughput(steps, warmup, sample_batch):
+    """The reference's CPU path for this workload (oracle port: torchvision/torch.nn restatement of model.py +
+    utils.get_loss + torch.optim.SGD, oracle/model_oracle.py) on all host cores.  Returns (clips/s, cores, sample)."""
+    import torch
+    from oracle.model_oracle import OracleAVModel, oracle_train_step
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(31)
+    model = OracleAVModel(CFG["hc"], CFG["K"]).train()
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-5)
+    video, spec, labels = synthetic_batch(torch, 0, sample_batch)
+    for _ in range(warmup):
+        oracle_train_step(model, opt, video, spec, labels, CFG["hc"])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = oracle_train_step(model, opt, video, spec, labels, CFG["hc"])
+    float(loss)
+    dt = time.perf_counter() - t0
+    sample = (f"{steps} train step(s) of {sample_batch} clips (configs[1] shapes 3x{CFG['T']}x{CFG['HW']}x{CFG['HW']} + "
+              f"1x257x{CFG['spec_T']}, K={CFG['K']}, {CFG['hc']} heads) after {warmup} warm-up step(s), "
+              f"torch {torch.__version__} CPU, {cores} threads")
+    return sample_batch * steps / dt, cores, sample, dt / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_batch = 4
+    steps = max(1, min(args.steps, 3))
+    val, cores, sample, ms = cpu_train_throughput(steps, min(args.warmup, 1), sample_batch)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: train step, batch 16/GPU, 3x32x112x112 clips + 1x257x200 spectrograms, K=309, "
+                                   "10 heads", "reference_sample_batch": sample_batch},
+            "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from selavi_b200 import _lib, build, model as sv_model, ops
+    from selavi_b200.optim import SGD
+    from selavi_b200.sk_utils import SKComm, SKWorkspace, sk_solve_raw
+    from selavi_b200.utils import get_loss
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        build.build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    _lib.lib()
+    pk = peaks()
+    B, hc, K = args.batch, CFG["hc"], CFG["K"]
+
+    torch.manual_seed(31)
+    model = sv_model.load_model(vid_base_arch="r2plus1d_18", aud_base_arch="resnet9", pretrained=False, norm_feat=False,
+                                use_mlp=True, headcount=hc, num_classes=K)
+    if world > 1:
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)           # main.py:117-118
+    model = model.to(dev).train()
+    opt = SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-5)    # main.py:132-137
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)  # main.py:156
+    video_h, spec_h, labels_h = synthetic_batch(torch, rank, B)
+    video_h, spec_h, labels_h = video_h.pin_memory(), spec_h.pin_memory(), labels_h.pin_memory()
+    video_d, spec_d, labels_d = video_h.to(dev), spec_h.to(dev), labels_h.to(dev)
+
+    def train_step(video, spec, labels):
+        fv, fa = net(video, spec)
+        loss = 0.5 * get_loss(fv, labels, hc) + 0.5 * get_loss(fa, labels, hc)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        train_step(video_d, spec_d, labels_d)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    _lib.COUNT_CALLS = True
+    _lib.CALLS.clear()
+    ms_total = timed(lambda: train_step(video_d, spec_d, labels_d), args.steps)
+    launches = _lib.kernel_launches()
+    _lib.COUNT_CALLS = False
+
+    def e2e_step():
+        v = video_h.to(dev, non_blocking=True)
+        s = spec_h.to(dev, non_blocking=True)
+        lab = labels_h.to(dev, non_blocking=True)
+        return float(train_step(v, s, lab).item())
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- live per-kernel timing of one more step (CUDA events around every conv launch on the launching stream)
+    ops.PROFILE = []
+    train_step(video_d, spec_d, labels_d)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    agg = {}
+    for kind, flops, e0, e1 in prof:
+        a = agg.setdefault(kind, [0.0, 0.0, 0])
+        a[0] += flops
+        a[1] += e0.elapsed_time(e1)
+        a[2] += 1
+    ms_step = ms_total / args.steps
+    conv = [agg.get("conv_fwd", [0, 0, 0]), agg.get("conv_dgrad", [0, 0, 0])]
+    conv_flops, conv_ms, conv_n = sum(c[0] for c in conv), sum(c[1] for c in conv), sum(c[2] for c in conv)
+    wg = agg.get("conv_wgrad", [0.0, 0.0, 0])
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    from selavi_b200 import engine
+    roofline = {"kernel": "conv_igemm_kernel (forward + data-gradient launches)", "bound": "tensor", "achieved": achieved,
+                "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"], "traffic": None,
+                "peak_source": f"{pk['src']} bf16 dense sustained", "launches_per_step": conv_n,
+                "avg_launch_ms": conv_ms / max(conv_n, 1), "share_of_step": conv_ms / ms_step,
+                "mma_passes": engine.PASSES, "issued_mma_tflops": achieved * engine.PASSES,
+                "wgrad_kernel": {"achieved": (wg[0] / (wg[1] * 1e-3) / 1e12) if wg[1] > 0 else 0.0, "unit": "TFLOP/s",
+                                 "launches_per_step": wg[2], "share_of_step": wg[1] / ms_step}}
+
+    # ---- Sinkhorn-Knopp: cfg-5 matrix, rows sharded over ranks, exactly 100 iterations (convergence test computed)
+    sk = None
+    try:
+        N, iters = 200000, 100
+        n_local = N // world
+        g = torch.Generator(device=dev).manual_seed(rank)
+        PS = torch.softmax(torch.randn(n_local, K, dtype=torch.float64, device=dev, generator=g), 1) * \
+            torch.softmax(torch.randn(n_local, K, dtype=torch.float64, device=dev, generator=g), 1)
+        ws = SKWorkspace(K, n_local, dev)
+        comm = SKComm(K) if world > 1 else None
+        kw = dict(world=world, rank=rank, peer_sum=comm.sum.peer_ptrs, peer_flag=comm.flag.peer_ptrs) if comm else {}
+
+        def sk_run(prep, n):
+            if comm:
+                comm.reset()
+            sk_solve_raw(PS, n_local * world, 20.0, None, ws, max_iters=n, stop_on_converge=False, do_prep=prep,
+                         do_final=False, **kw)
+
+        sk_run(True, 10)
+        for _ in range(3):
+            sk_run(False, iters)
+        ms_sk = min(timed(lambda: sk_run(False, iters), 1) for _ in range(3))
+        bytes_iter = n_local * K * 8
+        gbs = bytes_iter * iters / (ms_sk * 1e-3) / 1e9
+        sk = {"iters_per_sec": iters / (ms_sk * 1e-3), "N": n_local * world, "K": K, "iters": iters, "rows_per_gpu": n_local,
+              "roofline": {"kernel": "sk_kernel", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                           "frac": gbs / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+                           "note": "per GPU; shards below ~126 MB are L2-resident, so frac can exceed 1"}}
+    except Exception as e:  # noqa: BLE001
+        sk = {"error": repr(e)[:300]}
+
+    if rank == 0:
+        global_batch = B * world
+        value = global_batch / (ms_step * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "tf32x3 (fp32-accurate split tf32 MMA, fp32 accumulate/storage)" if engine.PASSES == 3 else "tf32",
+                "data": "synthetic",
+                "config": {"workload": "configs[1]: train step (video R(2+1)D-18 + audio ResNet-9 fwd/bwd, 20 MLP heads, CE, SGD), "
+                                       "per-GPU batch 16, clips 3x32x112x112, spectrograms 1x257x200, K=309, 10 heads",
+                           "global_batch": global_batch, "parallelism": f"dp{world}", "l2": "inputs_exceed_l2 (16 GB of activations per step)",
+                           "sk": "timed separately (key 'sk'): cfg-5 matrix, 100 iterations"},
+                "e2e": {"value": global_batch / (ms_e2e / args.steps * 1e-3), "unit": "clips/s",
+                        "h2d_bytes_per_step": int(video_h.numel() * 4 + spec_h.numel() * 4 + labels_h.numel() * 8),
+                        "d2h_bytes_per_step": 4},
+                "gpu_launches": launches, "roofline": roofline, "sk": sk, "clocks": clocks,
+                "algorithmic_tflops": FLOP_PER_SAMPLE_STEP * B / (ms_step * 1e-3) / 1e12}
+        if world == 1 and not args.no_cpu_baseline:
+            val, cores, sample, _ = cpu_train_throughput(1, 1, 2)
+            line["cpu_baseline"] = {"value": val, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=CFG["batch"], help="per-GPU batch (configs[1]: 16)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -86,6 +86,45 @@ class SelaviError(RuntimeError):
     pass
 
 
+# kernels launched per C-ABI call (for bench.py's `gpu_launches` claim); host-only queries launch none
+KERNELS_PER_CALL = {
+    "selavi_sk_solve": 1, "selavi_conv_pack_weights": 1, "selavi_conv_gemm": 1, "selavi_conv_wgrad": 2,
+    "selavi_bn_reduce_partials": 1, "selavi_bn_finalize": 1, "selavi_bn_eval_affine": 1, "selavi_bn_apply": 1,
+    "selavi_bn_bwd_reduce": 2, "selavi_bn_bwd_apply": 1, "selavi_relu_bwd": 1, "selavi_maxpool3x3s2_fwd": 1,
+    "selavi_maxpool3x3s2_bwd": 1, "selavi_avgpool_fwd": 1, "selavi_avgpool_bwd": 1, "selavi_nchw_to_cl": 1,
+    "selavi_sgd_step": 1, "selavi_bgemm": 1, "selavi_heads_bn_stats": 1, "selavi_heads_bn_finalize": 1,
+    "selavi_heads_bn_eval_affine": 1, "selavi_heads_act": 1, "selavi_heads_bn_bwd_reduce": 1,
+    "selavi_heads_bn_bwd_apply": 1, "selavi_heads_sum_masked": 1, "selavi_heads_colsum": 1, "selavi_ce_loss": 2,
+    "selavi_debug_umma_probe": 1,
+}
+COUNT_CALLS = False
+CALLS = {}
+
+
+def kernel_launches():
+    """Number of OUR kernels launched since CALLS was cleared (counted at the C-ABI boundary)."""
+    return sum(KERNELS_PER_CALL.get(k, 0) * v for k, v in CALLS.items())
+
+
+class _Handle:
+    """Attribute access to the typed ctypes functions, with optional call counting."""
+
+    def __init__(self, h):
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+            setattr(self, name, self._wrap(name, fn))
+
+    @staticmethod
+    def _wrap(name, fn):
+        def call(*a):
+            if COUNT_CALLS:
+                CALLS[name] = CALLS.get(name, 0) + 1
+            return fn(*a)
+        return call
+
+
 def lib():
     """Load (once) and return the ctypes handle; raises if the CUDA extension is not built."""
     global _lib
@@ -94,12 +133,7 @@ def lib():
             raise SelaviError(
                 f"{LIB_PATH} not found: build it with `python -m selavi_b200.build` "
                 "(no CPU fallback exists for the selavi_b200 hot path)")
-        h = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(h, name)
-            fn.restype = res
-            fn.argtypes = args
-        _lib = h
+        _lib = _Handle(ctypes.CDLL(LIB_PATH))
     return _lib
 
 

@@ -12,6 +12,27 @@ import torch
 from . import _lib
 
 
+# bench.py sets PROFILE to a list: every conv launch is then bracketed by CUDA events on the launching stream
+PROFILE = None
+
+
+class _Prof:
+    def __init__(self, kind, geom):
+        self.on = PROFILE is not None
+        if self.on:
+            self.kind, self.flops = kind, 2.0 * geom.m_out * geom.co * geom.ci * geom.taps
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def __enter__(self):
+        if self.on:
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if self.on:
+            self.e1.record()
+            PROFILE.append((self.kind, self.flops, self.e0, self.e1))
+
+
 def pad4(c):
     return (c + 3) & ~3
 
@@ -103,7 +124,7 @@ def conv_forward(x, wpack, geom, out=None, scale=None, shift=None, relu=False, s
     if out is None:
         out = torch.empty(geom.out_shape(), dtype=torch.float32, device=x.device)
     _chk(out, geom.out_shape(), "out")
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _Prof("conv_fwd", geom):
         _lib.check(_lib.lib().selavi_conv_gemm(_lib.ptr(x), _lib.ptr(out), _lib.ptr(wpack), geom.arr(0), _lib.ptr(scale),
                                                _lib.ptr(shift), 1 if relu else 0, _lib.ptr(stats), 0, passes,
                                                _lib.stream_ptr()), "selavi_conv_gemm(fwd)")
@@ -116,7 +137,7 @@ def conv_dgrad(dz, wpack_t, geom, out=None, accumulate=False, passes=3):
         out = torch.empty(geom.in_shape(), dtype=torch.float32, device=dz.device)
         accumulate = False
     _chk(out, geom.in_shape(), "dx")
-    with torch.cuda.device(dz.device):
+    with torch.cuda.device(dz.device), _Prof("conv_dgrad", geom):
         _lib.check(_lib.lib().selavi_conv_gemm(_lib.ptr(dz), _lib.ptr(out), _lib.ptr(wpack_t), geom.arr(1), None, None, 0,
                                                None, 1 if accumulate else 0, passes, _lib.stream_ptr()),
                    "selavi_conv_gemm(dgrad)")
@@ -139,7 +160,7 @@ def conv_wgrad(x, dz, geom, dw, scale=None, shift=None, relu=False, accumulate=F
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         _wgrad_ws[key] = ws
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _Prof("conv_wgrad", geom):
         _lib.check(lib.selavi_conv_wgrad(_lib.ptr(x), _lib.ptr(dz), _lib.ptr(dw), geom.arr(0), geom.ci, _lib.ptr(scale),
                                          _lib.ptr(shift), 1 if relu else 0, _lib.ptr(ws), 1 if accumulate else 0, passes,
                                          _lib.stream_ptr()), "selavi_conv_wgrad")

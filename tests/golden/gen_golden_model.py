@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 # name: (B, T, HW, spec_T, K, headcount)
 CONFIGS = {
     "cfg1": (2, 8, 112, 99, 28, 1),          # BASELINE.json configs[0]
-    "mini_cfg2": (2, 4, 64, 40, 309, 3),     # multi-head / K=309 shape at reduced size
+    "mini_cfg2": (4, 4, 64, 40, 309, 3),     # multi-head / K=309 shape at reduced size, well-conditioned batch
 }
 SMALL = ("bn", "bias", "mlp_v.block_forward.8", "mlp_a.block_forward.8", "mlp_v0.block_forward.8", "stem.0.weight",
          "audio_network.base.conv1.weight", "downsample.0.weight")
@@ -29,6 +29,13 @@ def make_inputs(name):
     video = rng.standard_normal((B, 3, T, HW, HW)).astype(np.float32)
     spec = (rng.standard_normal((B, 1, 257, ST)) * 17.89 + 1.93).astype(np.float32)
     labels = rng.integers(0, K, size=(B, hc)).astype(np.int64)
+    if name != "cfg1":
+        # Train-mode BatchNorm1d over a handful of near-identical clips (white noise through a random network) divides
+        # by a near-zero batch variance and amplifies rounding noise ~100x (cfg1 is kept as BASELINE.json states it).
+        # Real clips differ in brightness/contrast/loudness: give every clip its own gain and offset.
+        gain = (0.5 + 0.5 * np.arange(B, dtype=np.float32)).reshape(B, 1, 1, 1)
+        video = video * gain[..., None] + 0.3 * (np.arange(B, dtype=np.float32).reshape(B, 1, 1, 1, 1) - 1)
+        spec = spec * gain + 4.0 * (np.arange(B, dtype=np.float32).reshape(B, 1, 1, 1) - 1)
     return video, spec, labels
 
 
