@@ -51,17 +51,18 @@ class ConvRec:
     __slots__ = ("conv", "bn", "geom", "inp", "z", "scale", "shift", "mean", "invstd", "count")
 
 
-_pack_cache = {}
-
-
-def _packed(weight, geom, mode):
-    key = (weight.data_ptr(), mode, geom.ci, geom.co, geom.taps)
-    ver = weight._version
-    hit = _pack_cache.get(key)
-    if hit is not None and hit[0] == ver:
+def _packed(conv, geom, mode):
+    """Packed (pre-tiled, pre-swizzled, tf32 hi/lo) B operand of `conv.weight`, cached ON the module and
+    re-packed whenever the parameter storage or its version counter changes (optimizer step, load_state_dict,
+    .to(device), match_order's row permutation)."""
+    weight = conv.weight
+    cache = conv.__dict__.setdefault("_sv_pack", {})
+    tag = (weight.data_ptr(), weight._version)
+    hit = cache.get(mode)
+    if hit is not None and hit[0] == tag:
         return hit[1]
-    buf = ops.pack_weights(weight, geom, mode, out=hit[1] if hit is not None else None)
-    _pack_cache[key] = (ver, buf)
+    buf = ops.pack_weights(weight, geom, mode, out=hit[1] if (hit is not None and hit[1].device == weight.device) else None)
+    cache[mode] = (tag, buf)
     return buf
 
 
@@ -85,7 +86,7 @@ class TowerRunner:
         x = act.t
         nb, t, h, w, _ = x.shape
         geom = _geom_of(conv, nb, (t, h, w))
-        wp = _packed(conv.weight, geom, 0)
+        wp = _packed(conv, geom, 0)
         dev = x.device
         cs = geom.cos
         scale = torch.empty(cs, dtype=torch.float32, device=dev)
@@ -239,7 +240,7 @@ class TowerRunner:
             grads[conv.weight] = dw
         if not want_dx:
             return None
-        wpt = _packed(conv.weight, geom, 1)
+        wpt = _packed(conv, geom, 1)
         return ops.conv_dgrad(dz, wpt, geom, out=dx_out, accumulate=dx_accumulate, passes=PASSES)
 
     def backward(self, tape, dfeat, grads):
