@@ -40,6 +40,8 @@ const char* selavi_last_error(void);
  *             must be zero on every rank when the call starts.  world == 1: pass NULL.
  * Replaces the NCCL all-gather + rank-0 solve of src/sk_utils.py:214-242,287-327.
  */
+/* PS[n,k] = softmax_f64(logits_v[n,:])[k] * softmax_f64(logits_a[n,:])[k]  (src/sk_utils.py:206-211,309-315) */
+int selavi_sk_softmax_product(const float* logits_v, const float* logits_a, long long n, int K, double* PS, void* stream);
 size_t selavi_sk_workspace_bytes(int K);
 int selavi_sk_kp(int K);
 int selavi_sk_solve(double* PS, long long n_local, long long n_global, int K, double lamb, int use_dist,
@@ -152,6 +154,15 @@ int selavi_heads_sum_masked(const float* x, const float* mask, float* out, int H
 int selavi_heads_colsum(const float* x, float* out, int H, int M, int N, void* stream);
 int selavi_ce_loss(const void* const* logit_tbl, const long long* labels, long long lab_stride_b, long long lab_stride_h,
                    int H, int B, int K, float grad_scale, float* loss_rows, float* loss_mean, float* dlogits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Mel-spectrogram front end (datasets/audio_utils.py:47-63 -> python_speech_features.logfbank): pre-emphasis,
+ * framing (rectangular window, zero padded), 1024-point FFT, |X|^2/NFFT, triangular mel filterbank given by its
+ * floored bin edges bins[nfilt+2], eps floor, log, optional (x-1.93)/17.89.  signal [batch, samples] float64,
+ * out [batch, 1, nfilt, numframes] float32.
+ */
+int selavi_mel_logfbank(const double* signal, int batch, long long samples, int frame_len, int frame_step, int numframes,
+                        const double* bins, int nfilt, int nfft, double preemph, int z_normalize, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Symmetric peer-mapped buffers (CUDA IPC), the transport of the in-kernel NVSwitch exchange.

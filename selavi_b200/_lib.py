@@ -22,6 +22,7 @@ c_size_t = ctypes.c_size_t
 SIGNATURES = {
     "selavi_version": (c_int, []),
     "selavi_last_error": (ctypes.c_char_p, []),
+    "selavi_sk_softmax_product": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
     "selavi_sk_workspace_bytes": (c_size_t, [c_int]),
     "selavi_sk_kp": (c_int, [c_int]),
     "selavi_sk_solve": (c_int, [c_void_p, c_ll, c_ll, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -72,6 +73,8 @@ SIGNATURES = {
     "selavi_heads_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "selavi_ce_loss": (c_int, [c_void_p, c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
+    "selavi_mel_logfbank": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p, c_int, c_int, c_double, c_int,
+                                    c_void_p, c_void_p]),
     "selavi_debug_umma_probe": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.c_ulonglong, ctypes.c_ulonglong,
                                         ctypes.c_uint, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "selavi_symm_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
@@ -88,14 +91,14 @@ class SelaviError(RuntimeError):
 
 # kernels launched per C-ABI call (for bench.py's `gpu_launches` claim); host-only queries launch none
 KERNELS_PER_CALL = {
-    "selavi_sk_solve": 1, "selavi_conv_pack_weights": 1, "selavi_conv_gemm": 1, "selavi_conv_wgrad": 2,
+    "selavi_sk_solve": 1, "selavi_sk_softmax_product": 1, "selavi_conv_pack_weights": 1, "selavi_conv_gemm": 1, "selavi_conv_wgrad": 2,
     "selavi_bn_reduce_partials": 1, "selavi_bn_finalize": 1, "selavi_bn_eval_affine": 1, "selavi_bn_apply": 1,
     "selavi_bn_bwd_reduce": 2, "selavi_bn_bwd_apply": 1, "selavi_relu_bwd": 1, "selavi_maxpool3x3s2_fwd": 1,
     "selavi_maxpool3x3s2_bwd": 1, "selavi_avgpool_fwd": 1, "selavi_avgpool_bwd": 1, "selavi_nchw_to_cl": 1,
     "selavi_sgd_step": 1, "selavi_bgemm": 1, "selavi_heads_bn_stats": 1, "selavi_heads_bn_finalize": 1,
     "selavi_heads_bn_eval_affine": 1, "selavi_heads_act": 1, "selavi_heads_bn_bwd_reduce": 1,
     "selavi_heads_bn_bwd_apply": 1, "selavi_heads_sum_masked": 1, "selavi_heads_colsum": 1, "selavi_ce_loss": 2,
-    "selavi_debug_umma_probe": 1,
+    "selavi_debug_umma_probe": 1, "selavi_mel_logfbank": 1,
 }
 COUNT_CALLS = False
 CALLS = {}

@@ -495,6 +495,48 @@ int pick_kpl(int K) {
 
 }  // namespace
 
+namespace {
+// PS[n,k] = softmax64(v[n,:])[k] * softmax64(a[n,:])[k]   (src/sk_utils.py:206-211,309-315: f64 softmax of both
+// modalities' head outputs, then PS_v *= PS_a) — one warp per row, fp32 logits in, float64 out, one pass.
+__global__ void sk_softmax_product_kernel(const float* __restrict__ v, const float* __restrict__ a, long long n, int K,
+                                          double* __restrict__ PS) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float* vr = v + (size_t)row * K;
+    const float* ar = a + (size_t)row * K;
+    double mv = -INFINITY, ma = -INFINITY;
+    for (int k = lane; k < K; k += 32) {
+        mv = fmax(mv, (double)vr[k]);
+        ma = fmax(ma, (double)ar[k]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mv = fmax(mv, __shfl_xor_sync(0xffffffffu, mv, o));
+        ma = fmax(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+    }
+    double sv_ = 0.0, sa_ = 0.0;
+    for (int k = lane; k < K; k += 32) {
+        sv_ += exp((double)vr[k] - mv);
+        sa_ += exp((double)ar[k] - ma);
+    }
+    sv_ = warp_sum(sv_);
+    sa_ = warp_sum(sa_);
+    double* out = PS + (size_t)row * K;
+    for (int k = lane; k < K; k += 32) out[k] = (exp((double)vr[k] - mv) / sv_) * (exp((double)ar[k] - ma) / sa_);
+}
+}  // namespace
+
+extern "C" int selavi_sk_softmax_product(const float* logits_v, const float* logits_a, long long n, int K, double* PS,
+                                         void* stream) {
+    if (!logits_v || !logits_a || !PS || n <= 0 || K <= 0) return selavi_fail(-1, "sk_softmax_product: bad arguments");
+    const int warps = 8;
+    const long long blocks = (n + warps - 1) / warps;
+    sk_softmax_product_kernel<<<(unsigned)blocks, warps * 32, 0, (cudaStream_t)stream>>>(logits_v, logits_a, n, K, PS);
+    SV_CUDA_CHECK(cudaGetLastError(), "sk_softmax_product: launch");
+    return 0;
+}
+
 extern "C" int selavi_sk_kp(int K) {
     const int kpl = pick_kpl(K);
     return kpl < 0 ? -1 : kpl * 32 + 32;

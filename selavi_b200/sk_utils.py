@@ -18,7 +18,8 @@ import torch
 from . import _lib
 from .symm import SymmetricBuffer
 
-__all__ = ["optimize_L_sk_gpu", "optimize_L_sk_multi", "optimize_L_sk_sharded", "sk_solve_raw", "SKWorkspace"]
+__all__ = ["optimize_L_sk_gpu", "optimize_L_sk_multi", "optimize_L_sk_sharded", "sk_solve_raw", "SKWorkspace", "SKComm",
+           "softmax_product", "get_cluster_assignments_gpu", "cluster", "match_order", "shard_range", "assemble_labels"]
 
 
 class SKWorkspace:
@@ -148,3 +149,197 @@ def optimize_L_sk_sharded(args, PS_local, hc, n_global, comm, logger=None, kdist
     if args.rank == 0 and logger is not None:
         logger.info(f"error: {float(ws.err.item())}, step : {int(ws.iters.item())}")
     return cost, ws.labels
+
+
+# ====================================================================================================
+# Dataset-wide feature sweep + label assignment (src/sk_utils.py:23-356), row-sharded
+# ====================================================================================================
+def softmax_product(logits_v, logits_a):
+    """float64 softmax(v) * softmax(a) in one pass (src/sk_utils.py:206-211,309-315)."""
+    if not (logits_v.is_cuda and logits_v.dtype == torch.float32 and logits_a.shape == logits_v.shape):
+        raise ValueError("softmax_product needs two float32 CUDA matrices of equal shape")
+    logits_v, logits_a = logits_v.contiguous(), logits_a.contiguous()
+    n, K = logits_v.shape
+    PS = torch.empty((n, K), dtype=torch.float64, device=logits_v.device)
+    with torch.cuda.device(PS.device):
+        _lib.check(_lib.lib().selavi_sk_softmax_product(_lib.ptr(logits_v), _lib.ptr(logits_a), n, K, _lib.ptr(PS),
+                                                        _lib.stream_ptr()), "selavi_sk_softmax_product")
+    return PS
+
+
+def shard_range(N, world_size, rank):
+    """Rows owned by `rank` (src/sk_utils.py:157-161): N // world_size each, the remainder is dropped."""
+    local = N // world_size
+    return rank * local, (rank + 1) * local
+
+
+def assemble_labels(L, idx_all, lab_all, head):
+    """L[idx, head] = labels for the gathered (index, label) pairs of all ranks (src/sk_utils.py:323)."""
+    L[idx_all.long(), head] = lab_all
+    return L
+
+
+_comm_cache = {}
+
+
+def _unwrap(model):
+    return model.module if hasattr(model, "module") else model
+
+
+def get_cluster_assignments_gpu(args, dataset, model, logger=None, writer=None, group=None, iter_num=0):
+    """Same contract as src/sk_utils.py:137-356 (returns L [N, headcount] int64 on every rank, model left in train
+    mode with return_features=False), different data flow: every rank keeps the features of ITS rows, applies the
+    heads locally, and the ranks solve Sinkhorn-Knopp jointly on the row-sharded matrix — only the K-vector of
+    column sums crosses NVSwitch (inside the solver kernel) and the labels are all-gathered at the end.  Nothing is
+    gathered to rank 0, and there is no per-batch barrier."""
+    import numpy as np
+    import torch.distributed as dist
+    from torch.utils.data.sampler import SubsetRandomSampler
+    distributed = dist.is_available() and dist.is_initialized()
+    world, rank = (dist.get_world_size(group), dist.get_rank(group)) if distributed else (1, 0)
+    net = _unwrap(model)
+    model.eval()
+    N = len(dataset)
+    lo, hi = shard_range(N, args.world_size, args.rank)
+    sampler = SubsetRandomSampler(torch.arange(lo, hi).int())
+    dataloader = torch.utils.data.DataLoader(dataset, batch_size=64, sampler=sampler, shuffle=False,
+                                             num_workers=args.workers, pin_memory=True, collate_fn=None)
+    if distributed:
+        dist.barrier(group=group)
+    assert args.ind_groups <= args.headcount
+    hc = args.headcount
+    if hc > 1:
+        net.return_features = True
+    dev = torch.device("cuda", torch.cuda.current_device())
+    L = torch.zeros((N, hc), dtype=torch.long, device=dev)
+    order_heads = list(range(hc))
+    np.random.shuffle(order_heads)
+    n_local = hi - lo
+    for hd_grp_idx in range(args.ind_groups):
+        # 1. sweep this rank's rows (fresh augmentations per head group, like the reference)
+        feats_v, feats_a, idxs = [], [], []
+        with torch.no_grad():
+            for batch in dataloader:
+                video, audio, _, idx, _ = batch
+                fv, fa = model(video.cuda(non_blocking=True), audio.cuda(non_blocking=True))
+                feats_v.append(fv.reshape(video.shape[0], -1))
+                feats_a.append(fa.reshape(video.shape[0], -1))
+                idxs.append(idx.cuda(non_blocking=True).long())
+        F_v, F_a, idx_local = torch.cat(feats_v), torch.cat(feats_a), torch.cat(idxs)
+        if args.match and iter_num == 0:
+            for head in order_heads[hd_grp_idx::args.ind_groups]:
+                head_a = net.mlp_a if hc == 1 else getattr(net, f"mlp_a{head}")
+                head_v = net.mlp_v if hc == 1 else getattr(net, f"mlp_v{head}")
+                with torch.no_grad():
+                    Pv = F_v if hc == 1 else head_v.forward(F_v)
+                    Pa = F_a if hc == 1 else head_a.forward(F_a)
+                match_order(args, Pv, Pa, list(head_a.modules())[-1] if net.use_mlp else head_a, logger=logger, group=group,
+                            logits=True)
+        # 2. joint row-sharded Sinkhorn-Knopp per head
+        _costs = [0 for _ in range(hc)]
+        for head in order_heads[hd_grp_idx::args.ind_groups]:
+            sk_start = time.time()
+            with torch.no_grad():
+                if hc == 1:
+                    lv, la = F_v, F_a            # logits of the single head (the reference softmaxes them, :206-211)
+                else:
+                    lv = getattr(net, f"mlp_v{head}").forward(F_v)
+                    la = getattr(net, f"mlp_a{head}").forward(F_a)
+                PS = softmax_product(lv, la)
+            if world > 1:
+                comm = _comm_cache.get((PS.shape[1], id(group)))
+                if comm is None:
+                    comm = SKComm(PS.shape[1], group)
+                    _comm_cache[(PS.shape[1], id(group))] = comm
+                cost, L_head = optimize_L_sk_sharded(args, PS, head, n_local * world, comm, logger=logger)
+                gathered_idx = [torch.empty_like(idx_local) for _ in range(world)]
+                gathered_lab = [torch.empty_like(L_head) for _ in range(world)]
+                dist.all_gather(gathered_idx, idx_local, group=group)
+                dist.all_gather(gathered_lab, L_head, group=group)
+                assemble_labels(L, torch.cat(gathered_idx), torch.cat(gathered_lab), head)
+            else:
+                cost, L_head = optimize_L_sk_gpu(args, PS, hc=head, logger=logger)
+                assemble_labels(L, idx_local, L_head, head)
+            _costs[head] = cost
+            if args.rank == 0 and logger is not None:
+                logger.info(f"Head {head}, Cost: (video): {cost:.3f}; time: {time.time() - sk_start:.3f}")
+        if args.rank == 0 and logger is not None:
+            logger.info(f"Final Cost: (video): {np.mean(_costs):.3f}")
+        if writer:
+            writer.add_scalar('train/LP-cost', np.mean(_costs), iter_num)
+    if distributed:
+        dist.barrier(group=group)
+    torch.cuda.synchronize()
+    net.return_features = False
+    model.train()
+    return L
+
+
+def l1_cost_matrix(P1, P2):
+    """C[i, j] = sum_n |P1[n, i] - P2[n, j]|  (the quantity `c(a, b)` of src/sk_utils.py:430-431 for all column pairs)."""
+    K = P1.shape[1]
+    C = torch.empty((K, K), dtype=torch.float64, device=P1.device)
+    P1, P2 = P1.to(torch.float64), P2.to(torch.float64)
+    for i0 in range(0, K, 16):           # chunked broadcast keeps the temporary at N*16*K elements
+        C[i0:i0 + 16] = (P1[:, i0:i0 + 16, None] - P2[:, None, :]).abs().sum(0)
+    return C
+
+
+@torch.no_grad()
+def match_order(args, emb1, emb2_in, W2, steps=50000, restarts=2, logger=None, group=None, logits=False):
+    """Same contract, RNG stream (np.random.choice) and result as src/sk_utils.py:424-467: random pair-swap
+    hill-climb minimising sum |emb1 - emb2[:, perm]|, then the rows of the audio head's last Linear are permuted.
+    Instead of ~10^5 x 15 tiny kernels with an .item() sync each, the K x K L1 cost matrix is computed once (rows
+    sharded over ranks, all-reduced) and the hill-climb runs on it on the host.
+    `logits=True`: inputs are this rank's head outputs; the float64 softmax (src/sk_utils.py:272-275) is applied here."""
+    import numpy as np
+    import torch.distributed as dist
+    distributed = dist.is_available() and dist.is_initialized()
+    if logits and emb1 is not None:
+        emb1 = torch.softmax(emb1.double(), dim=1)
+        emb2_in = torch.softmax(emb2_in.double(), dim=1)
+    K = len(W2.bias.data)
+    C = l1_cost_matrix(emb1, emb2_in)
+    if distributed and dist.get_world_size(group) > 1:
+        dist.all_reduce(C, group=group)
+    fin_perm = np.arange(K)
+    if args.rank == 0:
+        Cn = C.cpu().numpy()
+        ar = np.arange(K)
+        cost = Cn[ar, ar].sum()
+        best_cost = cost
+        if logger is not None:
+            logger.info(f'initial cost: {cost:.1f}')
+        last_iter = 0
+        for _ in range(restarts):
+            perm = np.arange(K)
+            for _iter in range(steps):
+                i, j = np.random.choice(K, 2, replace=False)
+                delta = (Cn[i, perm[i]] + Cn[j, perm[j]]) - (Cn[i, perm[j]] + Cn[j, perm[i]])
+                if delta > 0:
+                    perm[i], perm[j] = perm[j], perm[i]
+                    last_iter = _iter
+                if _iter - last_iter > 1000:
+                    break
+            cost_try = Cn[ar, perm].sum()
+            if logger is not None:
+                logger.info(f"cost of this try: {cost_try:.2f}")
+            if cost_try < best_cost:
+                best_cost = cost_try
+                fin_perm = perm.copy()
+        if logger is not None:
+            logger.info(f"final cost: {best_cost:.2f}")
+    fin = torch.from_numpy(fin_perm).to(W2.bias.device)
+    if distributed and dist.get_world_size(group) > 1:
+        dist.broadcast(fin, dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    W2.bias.data = W2.bias.data[fin]
+    W2.weight.data = W2.weight.data[fin]
+    return fin
+
+
+def cluster(args, selflabels, dataset, model, sk_counter, logger, writer, group, iter_num):
+    """src/sk_utils.py:23-134 without the CPU-side NMI/purity logging (out of scope): returns the
+    new labels on every rank."""
+    with torch.no_grad():
+        selflabels = get_cluster_assignments_gpu(args, dataset, model, logger, writer, group, iter_num)
+    return selflabels
