@@ -93,7 +93,7 @@ def cpu_train_throughput(steps, warmup, sample_batch):
     t0 = time.perf_counter()
     for _ in range(steps):
         loss = oracle_train_step(model, opt, video, spec, labels, CFG["hc"])
-    float(loss)
+    float(loss.detach())
     dt = time.perf_counter() - t0
     sample = (f"{steps} train step(s) of {sample_batch} clips (configs[1] shapes 3x{CFG['T']}x{CFG['HW']}x{CFG['HW']} + "
               f"1x257x{CFG['spec_T']}, K={CFG['K']}, {CFG['hc']} heads) after {warmup} warm-up step(s), "
@@ -142,8 +142,10 @@ def run_ours(args):
     B, hc, K = args.batch, CFG["hc"], CFG["K"]
 
     torch.manual_seed(31)
-    model = sv_model.load_model(vid_base_arch="r2plus1d_18", aud_base_arch="resnet9", pretrained=False, norm_feat=False,
-                                use_mlp=True, headcount=hc, num_classes=K)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):       # the reference's constructor prints; stdout carries ONE JSON line
+        model = sv_model.load_model(vid_base_arch="r2plus1d_18", aud_base_arch="resnet9", pretrained=False,
+                                    norm_feat=False, use_mlp=True, headcount=hc, num_classes=K)
     if world > 1:
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)           # main.py:117-118
     model = model.to(dev).train()

@@ -29,13 +29,14 @@ namespace {
 
 constexpr int BM = 128;            // pixels per tile (UMMA M)
 constexpr int BK = 32;             // fp32 elements per K stage (one 128B swizzle row)
-constexpr int LOADER_WARPS = 8;
-constexpr int LOADER_THREADS = LOADER_WARPS * 32;
-constexpr int MMA_WARP = LOADER_WARPS;
-constexpr int BPROD_WARP = LOADER_WARPS + 1;
-constexpr int CONV_THREADS = (LOADER_WARPS + 2) * 32;
+constexpr int EPI_WARPS = 4;       // warps 0..3  : epilogue (TMEM lane quadrant = warp id)
+constexpr int LOADER_WARPS = 8;    // warps 4..11 : A-operand gather
+constexpr int MMA_WARP = EPI_WARPS + LOADER_WARPS;
+constexpr int BPROD_WARP = MMA_WARP + 1;
+constexpr int CONV_THREADS = (BPROD_WARP + 1) * 32;
 constexpr int A_TILE_BYTES = BM * 128;
 constexpr int MAX_TAPS = 64;
+constexpr int MAX_STAGES = 6;
 
 struct ConvParams {
     const float* src;
@@ -49,11 +50,11 @@ struct ConvParams {
     int td, hd, wd, cd;          // dst geometry
     int kt, kh, kw, st, sh, sw, pt, ph, pw;
     int M;                       // nb*td*hd*wd
-    int kchunks;                 // taps * cs/4   (16-byte chunks along K)
-    int kstages;                 // ceil(kchunks / 8)
+    int m_tiles;
+    int kstages;                 // ceil(taps * cs/4 / 8)
     int bnt, ntiles, stages;
     int pro_relu, accumulate, passes;
-    uint32_t tmem_cols;
+    uint32_t tmem_cols;          // 2 accumulators of bnt columns, power of two
 };
 
 __device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
@@ -65,36 +66,55 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// One gathered K stage of a loader thread: 4 rows x one 16-byte chunk, plus the prologue affine of that chunk.
+struct AStage {
+    float4 v[4];
+    float4 sc, sf;
+    uint32_t okmask;  // bit j: row j valid for this tap (prologue applies, otherwise exact zero)
+};
+
+// Persistent kernel: CTA b processes tiles b, b+gridDim.x, ... (tile = m_tile * ntiles + n_tile).
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // carve: [stages x (A_hi | A_lo | B_hi | B_lo)] [barriers] [tap table] [stat scratch]
+    // carve: [stages x (A_hi | A_lo | B_hi | B_lo)] [barriers] [tap tables] [stat scratch]
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_tile_bytes = p.bnt * 128;
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * b_tile_bytes;
     unsigned char* tail = smem + (size_t)p.stages * stage_bytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);       // [stages]
-    uint64_t* empty_bar = full_bar + 8;                            // [stages]
-    uint64_t* accum_bar = empty_bar + 8;                           // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-    int* tap_dt = reinterpret_cast<int*>(tmem_slot + 2);           // [MAX_TAPS] packed (kt | kh<<8 | kw<<16)
-    float* s_stat = reinterpret_cast<float*>(tap_dt + MAX_TAPS);   // [LOADER_WARPS][2][16] per 16-col unit
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);        // [MAX_STAGES]
+    uint64_t* empty_bar = full_bar + MAX_STAGES;                    // [MAX_STAGES]
+    uint64_t* tfull_bar = empty_bar + MAX_STAGES;                   // [2] accumulator ready
+    uint64_t* tempty_bar = tfull_bar + 2;                           // [2] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    int* tap_dt = reinterpret_cast<int*>(tmem_slot + 2);            // [MAX_TAPS] packed (kt | kh<<8 | kw<<16)
+    int* tap_off = tap_dt + MAX_TAPS;                               // [MAX_TAPS] pixel offset of the tap
+    float* s_stat = reinterpret_cast<float*>(tap_off + MAX_TAPS);   // [EPI_WARPS][2][256]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * BM;
-    const int ntile = blockIdx.y;
     const int taps = p.kt * p.kh * p.kw;
+    const int total_tiles = p.m_tiles * p.ntiles;
 
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) {
             sv::mbar_init(&full_bar[s], LOADER_WARPS + 1);
             sv::mbar_init(&empty_bar[s], 1);
         }
-        sv::mbar_init(accum_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            sv::mbar_init(&tfull_bar[a], 1);
+            sv::mbar_init(&tempty_bar[a], EPI_WARPS);
+        }
         sv::fence_barrier_init();
     }
     for (int t = tid; t < taps; t += CONV_THREADS) {
         const int kw_ = t % p.kw, kh_ = (t / p.kw) % p.kh, kt_ = t / (p.kw * p.kh);
         tap_dt[t] = kt_ | (kh_ << 8) | (kw_ << 16);
+        if (p.mode == 0) {
+            tap_off[t] = (kt_ * p.hs + kh_) * p.ws + kw_;
+        } else {
+            // transposed gather: src = (dst + pad - k) / stride  ==  floor((dst+pad)/stride) - (k >> log2(stride)) when valid
+            const int qt = p.st == 2 ? (kt_ >> 1) : kt_, qh = p.sh == 2 ? (kh_ >> 1) : kh_, qw = p.sw == 2 ? (kw_ >> 1) : kw_;
+            tap_off[t] = -((qt * p.hs + qh) * p.ws + qw);
+        }
     }
     if (warp == MMA_WARP) {
         sv::tmem_alloc(tmem_slot, p.tmem_cols);
@@ -105,253 +125,302 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
     sv::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < LOADER_WARPS) {
-        // ------------------------------------------------------------------ A loaders
-        const int c = tid & 7;    // 16-byte chunk within the 128B K row
-        const int r0 = tid >> 3;  // rows r0 + 32*j
+    if (warp >= EPI_WARPS && warp < MMA_WARP) {
+        // ------------------------------------------------------------------ A loaders (256 threads)
+        const int ltid = tid - EPI_WARPS * 32;
+        const int c = ltid & 7;    // 16-byte chunk within the 128B K row
+        const int r0 = ltid >> 3;  // rows r0 + 32*j
         const int C4 = p.cs >> 2;
-        int pixn[4];              // n * (ts*hs*ws) or -1 when the row is past M
-        int dcoord[4];            // packed dst coords t | h<<10 | w<<21
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int m = m0 + r0 + 32 * j;
-            if (m < p.M) {
-                int w_ = m % p.wd;
-                int t1 = m / p.wd;
-                int h_ = t1 % p.hd;
-                int t2 = t1 / p.hd;
-                int t_ = t2 % p.td;
-                int n_ = t2 / p.td;
-                pixn[j] = n_ * (p.ts * p.hs * p.ws);
-                dcoord[j] = t_ | (h_ << 10) | (w_ << 21);
-            } else {
-                pixn[j] = -1;
-                dcoord[j] = 0;
-            }
-        }
-        int tap = 0, c4 = c;  // flattened K chunk q = 8*ks + c  ->  (tap, c4)
-        while (c4 >= C4) {
-            c4 -= C4;
-            ++tap;
-        }
         const uint32_t sw_off = (uint32_t)((c ^ (r0 & 7)) << 4);
+        const bool pro = p.pro_scale != nullptr;
         int stage = 0;
         uint32_t phase = 0;
-        for (int ks = 0; ks < p.kstages; ++ks) {
-            // issue the gathers first (they do not depend on the smem slot), then wait for the slot
-            float4 v[4];
-            bool okv[4];
-            const bool kvalid = tap < taps;
-            int kt_ = 0, kh_ = 0, kw_ = 0;
-            if (kvalid) {
-                const int pk = tap_dt[tap];
-                kt_ = pk & 255;
-                kh_ = (pk >> 8) & 255;
-                kw_ = (pk >> 16) & 255;
-            }
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m0 = (tile / p.ntiles) * BM;
+            // per-row gather base (pixel index of tap 0) and per-dimension tap validity bits
+            int pb[4];
+            uint32_t vm[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                bool ok = kvalid && pixn[j] >= 0;
-                int t_ = dcoord[j] & 1023, h_ = (dcoord[j] >> 10) & 2047, w_ = (dcoord[j] >> 21) & 1023;
-                int a, b, d;
-                if (p.mode == 0) {
-                    a = t_ * p.st - p.pt + kt_;
-                    b = h_ * p.sh - p.ph + kh_;
-                    d = w_ * p.sw - p.pw + kw_;
-                } else {
-                    a = t_ + p.pt - kt_;
-                    b = h_ + p.ph - kh_;
-                    d = w_ + p.pw - kw_;
-                    if (p.st == 2) { ok &= !(a & 1); a >>= 1; }
-                    if (p.sh == 2) { ok &= !(b & 1); b >>= 1; }
-                    if (p.sw == 2) { ok &= !(d & 1); d >>= 1; }
-                }
-                ok &= (a >= 0) & (a < p.ts) & (b >= 0) & (b < p.hs) & (d >= 0) & (d < p.ws);
-                if (ok) {
-                    const size_t pix = (size_t)(pixn[j] + (a * p.hs + b) * p.ws + d);
-                    v[j] = __ldg(reinterpret_cast<const float4*>(p.src + pix * p.cs + c4 * 4));
-                }
-                okv[j] = ok;
-            }
-            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sf = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.pro_scale != nullptr && kvalid) {
-                sc = __ldg(reinterpret_cast<const float4*>(p.pro_scale + c4 * 4));
-                sf = __ldg(reinterpret_cast<const float4*>(p.pro_shift + c4 * 4));
-            }
-            sv::mbar_wait(&empty_bar[stage], phase ^ 1);
-            const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint32_t a_lo = a_hi + A_TILE_BYTES;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float4 x = v[j];
-                if (p.pro_scale != nullptr && okv[j]) {
-                    x.x = fmaf(x.x, sc.x, sf.x);
-                    x.y = fmaf(x.y, sc.y, sf.y);
-                    x.z = fmaf(x.z, sc.z, sf.z);
-                    x.w = fmaf(x.w, sc.w, sf.w);
-                    if (p.pro_relu) {
-                        x.x = fmaxf(x.x, 0.f);
-                        x.y = fmaxf(x.y, 0.f);
-                        x.z = fmaxf(x.z, 0.f);
-                        x.w = fmaxf(x.w, 0.f);
+                const int m = m0 + r0 + 32 * j;
+                pb[j] = 0;
+                vm[j] = 0;
+                if (m < p.M) {
+                    const int w_ = m % p.wd;
+                    const int t1 = m / p.wd;
+                    const int h_ = t1 % p.hd;
+                    const int t2 = t1 / p.hd;
+                    const int t_ = t2 % p.td;
+                    const int n_ = t2 / p.td;
+                    int bt, bh, bw;
+                    uint32_t mt = 0, mh = 0, mw = 0;
+                    if (p.mode == 0) {
+                        bt = t_ * p.st - p.pt;
+                        bh = h_ * p.sh - p.ph;
+                        bw = w_ * p.sw - p.pw;
+                        for (int k = 0; k < p.kt; ++k) mt |= (uint32_t)((bt + k >= 0) & (bt + k < p.ts)) << k;
+                        for (int k = 0; k < p.kh; ++k) mh |= (uint32_t)((bh + k >= 0) & (bh + k < p.hs)) << k;
+                        for (int k = 0; k < p.kw; ++k) mw |= (uint32_t)((bw + k >= 0) & (bw + k < p.ws)) << k;
+                    } else {
+                        const int at = t_ + p.pt, ah = h_ + p.ph, aw = w_ + p.pw;
+                        for (int k = 0; k < p.kt; ++k) {
+                            int u = at - k;
+                            bool ok = u >= 0;
+                            if (p.st == 2) { ok &= !(u & 1); u >>= 1; }
+                            mt |= (uint32_t)(ok & (u < p.ts)) << k;
+                        }
+                        for (int k = 0; k < p.kh; ++k) {
+                            int u = ah - k;
+                            bool ok = u >= 0;
+                            if (p.sh == 2) { ok &= !(u & 1); u >>= 1; }
+                            mh |= (uint32_t)(ok & (u < p.hs)) << k;
+                        }
+                        for (int k = 0; k < p.kw; ++k) {
+                            int u = aw - k;
+                            bool ok = u >= 0;
+                            if (p.sw == 2) { ok &= !(u & 1); u >>= 1; }
+                            mw |= (uint32_t)(ok & (u < p.ws)) << k;
+                        }
+                        bt = p.st == 2 ? (at >> 1) : at;
+                        bh = p.sh == 2 ? (ah >> 1) : ah;
+                        bw = p.sw == 2 ? (aw >> 1) : aw;
                     }
-                }
-                const uint32_t row_off = (uint32_t)((r0 + 32 * j) * 128) + sw_off;
-                const uint32_t h0 = tf32_hi(x.x), h1 = tf32_hi(x.y), h2 = tf32_hi(x.z), h3 = tf32_hi(x.w);
-                st_shared_v4(a_hi + row_off, h0, h1, h2, h3);
-                if (p.passes == 3) {
-                    st_shared_v4(a_lo + row_off, __float_as_uint(x.x - __uint_as_float(h0)),
-                                 __float_as_uint(x.y - __uint_as_float(h1)), __float_as_uint(x.z - __uint_as_float(h2)),
-                                 __float_as_uint(x.w - __uint_as_float(h3)));
+                    pb[j] = ((n_ * p.ts + bt) * p.hs + bh) * p.ws + bw;
+                    vm[j] = mt | (mh << 8) | (mw << 16) | 0x80000000u;
                 }
             }
-            sv::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) sv::mbar_arrive(&full_bar[stage]);
-            // advance K position by 8 chunks
-            c4 += 8;
-            while (c4 >= C4 && tap < taps) {
+            int tap = 0, c4 = c;  // flattened K chunk q = 8*ks + c  ->  (tap, c4)
+            while (c4 >= C4) {
                 c4 -= C4;
                 ++tap;
             }
-            if (++stage == p.stages) {
-                stage = 0;
-                phase ^= 1;
-            }
-        }
-
-        // ------------------------------------------------------------------ epilogue (same 8 warps)
-        sv::mbar_wait(accum_bar, 0);
-        sv::tc_fence_after();
-        const int quad = warp & 3, half = warp >> 2;
-        const int units = p.bnt >> 4;                   // 16-column units
-        const int u_begin = half == 0 ? 0 : (units + 1) / 2;
-        const int u_end = half == 0 ? (units + 1) / 2 : units;
-        const int m = m0 + quad * 32 + lane;
-        const bool row_ok = m < p.M;
-        const int n_base = ntile * p.bnt;
-        float* out_row = p.dst + (size_t)(row_ok ? m : 0) * p.cd;
-        for (int u = u_begin; u < u_end; ++u) {
-            uint32_t acc[16];
-            sv::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(u * 16), acc);
-            sv::tmem_ld_wait();
-            float f[16];
+            // issue the gathers of one K stage into registers (no dependence on the smem ring)
+            auto gather = [&](AStage& a) {
+                a.okmask = 0;
+                a.sc = make_float4(1.f, 1.f, 1.f, 1.f);
+                a.sf = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(acc[i]);
-            const int ncol = n_base + u * 16;
-            if (row_ok) {
+                for (int j = 0; j < 4; ++j) a.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tap < taps) {
+                    const int pk = tap_dt[tap];
+                    const int off = tap_off[tap];
+                    const int s_t = pk & 255, s_h = 8 + ((pk >> 8) & 255), s_w = 16 + ((pk >> 16) & 255);
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    if (ncol + i < p.cd) {
-                        float4* dp = reinterpret_cast<float4*>(out_row + ncol + i);
-                        float4 o = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                        if (p.accumulate) {
-                            const float4 old = *dp;
-                            o.x += old.x;
-                            o.y += old.y;
-                            o.z += old.z;
-                            o.w += old.w;
-                        }
-                        *dp = o;
-                    }
-                }
-            }
-            if (p.stats != nullptr) {
-                // column sums over this warp's 32 rows (rows past M hold exact zeros): transpose-reduce
-                float s1[16], s2[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    s1[i] = f[i];
-                    s2[i] = f[i] * f[i];
-                }
-#pragma unroll
-                for (int off = 16, n = 8; off >= 2; off >>= 1, n >>= 1) {
-                    const bool upper = (lane & off) != 0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (i < n) {
-                            const float send1 = upper ? s1[i] : s1[i + n];
-                            const float keep1 = upper ? s1[i + n] : s1[i];
-                            s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
-                            const float send2 = upper ? s2[i] : s2[i + n];
-                            const float keep2 = upper ? s2[i + n] : s2[i];
-                            s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t m_ = vm[j];
+                        if ((m_ >> 31) & (m_ >> s_t) & (m_ >> s_h) & (m_ >> s_w) & 1u) {
+                            a.v[j] = __ldg(reinterpret_cast<const float4*>(p.src + (size_t)(pb[j] + off) * p.cs + c4 * 4));
+                            a.okmask |= 1u << j;
                         }
                     }
+                    if (pro) {
+                        a.sc = __ldg(reinterpret_cast<const float4*>(p.pro_scale + c4 * 4));
+                        a.sf = __ldg(reinterpret_cast<const float4*>(p.pro_shift + c4 * 4));
+                    }
                 }
-                s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
-                s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
-                // lane L holds column (L >> 1) of this unit
-                float* sq = s_stat + (size_t)(warp * 2) * 16;
-                if ((lane & 1) == 0) {
-                    sq[lane >> 1] = s1[0];
-                    sq[16 + (lane >> 1)] = s2[0];
+                c4 += 8;  // advance the K position by 8 chunks
+                while (c4 >= C4 && tap < taps) {
+                    c4 -= C4;
+                    ++tap;
                 }
-                // the 4 quadrant warps of this column half combine (named barrier per half: 128 threads)
-                named_bar_sync(1 + half, 128);
-                if (quad == 0 && lane < 32) {
-                    const int which = lane >> 4, col = lane & 15;
-                    float tsum = 0.f;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) tsum += s_stat[(size_t)((half * 4 + q) * 2 + which) * 16 + col];
-                    const int ctot = p.ntiles * p.bnt;
-                    p.stats[((size_t)blockIdx.x * 2 + which) * ctot + ncol + col] = tsum;
-                }
-                named_bar_sync(1 + half, 128);
-            }
-        }
-        sv::tc_fence_before();
-    } else if (warp == MMA_WARP) {
-        // ------------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
-            const uint32_t idesc = sv::make_idesc_tf32(BM, p.bnt, 0, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int ks = 0; ks < p.kstages; ++ks) {
-                sv::mbar_wait(&full_bar[stage], phase);
-                sv::tc_fence_after();
+            };
+            // prologue + tf32 split + swizzled store of one gathered stage, then signal the MMA warp
+            auto commit = [&](const AStage& a) {
+                sv::mbar_wait(&empty_bar[stage], phase ^ 1);
                 const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint32_t a_lo = a_hi + A_TILE_BYTES;
-                const uint32_t b_hi = a_lo + A_TILE_BYTES;
-                const uint32_t b_lo = b_hi + b_tile_bytes;
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const uint64_t da_hi = sv::make_smem_desc_sw128(a_hi + k4 * 32, 16, 1024);
-                    const uint64_t db_hi = sv::make_smem_desc_sw128(b_hi + k4 * 32, 16, 1024);
+                for (int j = 0; j < 4; ++j) {
+                    float4 x = a.v[j];
+                    if (pro && ((a.okmask >> j) & 1u)) {
+                        x.x = fmaf(x.x, a.sc.x, a.sf.x);
+                        x.y = fmaf(x.y, a.sc.y, a.sf.y);
+                        x.z = fmaf(x.z, a.sc.z, a.sf.z);
+                        x.w = fmaf(x.w, a.sc.w, a.sf.w);
+                        if (p.pro_relu) {
+                            x.x = fmaxf(x.x, 0.f);
+                            x.y = fmaxf(x.y, 0.f);
+                            x.z = fmaxf(x.z, 0.f);
+                            x.w = fmaxf(x.w, 0.f);
+                        }
+                    }
+                    const uint32_t row_off = (uint32_t)((r0 + 32 * j) * 128) + sw_off;
+                    const uint32_t h0 = tf32_hi(x.x), h1 = tf32_hi(x.y), h2 = tf32_hi(x.z), h3 = tf32_hi(x.w);
+                    st_shared_v4(a_hi + row_off, h0, h1, h2, h3);
                     if (p.passes == 3) {
-                        const uint64_t da_lo = sv::make_smem_desc_sw128(a_lo + k4 * 32, 16, 1024);
-                        const uint64_t db_lo = sv::make_smem_desc_sw128(b_lo + k4 * 32, 16, 1024);
-                        sv::umma_tf32(tmem_base, da_lo, db_hi, idesc, (ks | k4) ? 1u : 0u);
-                        sv::umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
-                        sv::umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
-                    } else {
-                        sv::umma_tf32(tmem_base, da_hi, db_hi, idesc, (ks | k4) ? 1u : 0u);
+                        st_shared_v4(a_lo + row_off, __float_as_uint(x.x - __uint_as_float(h0)),
+                                     __float_as_uint(x.y - __uint_as_float(h1)), __float_as_uint(x.z - __uint_as_float(h2)),
+                                     __float_as_uint(x.w - __uint_as_float(h3)));
                     }
                 }
-                sv::umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+                sv::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) sv::mbar_arrive(&full_bar[stage]);
                 if (++stage == p.stages) {
                     stage = 0;
                     phase ^= 1;
                 }
+            };
+            // software pipeline: the gathers of stage ks+1 are in flight while stage ks is converted and stored
+            AStage sa, sb;
+            gather(sa);
+            for (int ks = 0; ks < p.kstages; ks += 2) {
+                if (ks + 1 < p.kstages) gather(sb);
+                commit(sa);
+                if (ks + 1 < p.kstages) {
+                    if (ks + 2 < p.kstages) gather(sa);
+                    commit(sb);
+                }
             }
-            sv::umma_commit(accum_bar);  // accumulator complete
+        }
+    } else if (warp < EPI_WARPS) {
+        // ------------------------------------------------------------------ epilogue (4 warps, one TMEM quadrant each)
+        const int quad = warp;
+        const int units = p.bnt >> 4;  // 16-column units
+        const int ctot = p.ntiles * p.bnt;
+        float* my_stat = s_stat + (size_t)warp * 512;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const int m_tile = tile / p.ntiles, ntile = tile % p.ntiles;
+            const int m = m_tile * BM + quad * 32 + lane;
+            const bool row_ok = m < p.M;
+            const int n_base = ntile * p.bnt;
+            float* out_row = p.dst + (size_t)(row_ok ? m : 0) * p.cd;
+            sv::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
+            sv::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * (p.tmem_cols >> 1);
+            for (int u = 0; u < units; ++u) {
+                uint32_t av[16];
+                sv::tmem_ld16(taddr + (uint32_t)(u * 16), av);
+                sv::tmem_ld_wait();
+                float f[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(av[i]);
+                const int ncol = n_base + u * 16;
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        if (ncol + i < p.cd) {
+                            float4* dp = reinterpret_cast<float4*>(out_row + ncol + i);
+                            float4 o = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                            if (p.accumulate) {
+                                const float4 old = *dp;
+                                o.x += old.x;
+                                o.y += old.y;
+                                o.z += old.z;
+                                o.w += old.w;
+                            }
+                            *dp = o;
+                        }
+                    }
+                }
+                if (p.stats != nullptr) {
+                    // column sums over this warp's 32 rows (rows past M hold exact zeros): transpose-reduce
+                    float s1[16], s2[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        s1[i] = f[i];
+                        s2[i] = f[i] * f[i];
+                    }
+#pragma unroll
+                    for (int off = 16, n = 8; off >= 2; off >>= 1, n >>= 1) {
+                        const bool upper = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (i < n) {
+                                const float send1 = upper ? s1[i] : s1[i + n];
+                                const float keep1 = upper ? s1[i + n] : s1[i];
+                                s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+                                const float send2 = upper ? s2[i] : s2[i + n];
+                                const float keep2 = upper ? s2[i + n] : s2[i];
+                                s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+                            }
+                        }
+                    }
+                    s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
+                    s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
+                    if ((lane & 1) == 0) {  // lane L holds column (L >> 1) of this unit
+                        my_stat[u * 16 + (lane >> 1)] = s1[0];
+                        my_stat[256 + u * 16 + (lane >> 1)] = s2[0];
+                    }
+                }
+            }
+            // accumulator drained: hand the TMEM buffer back to the MMA warp
+            sv::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) sv::mbar_arrive(&tempty_bar[acc]);
+            if (p.stats != nullptr) {
+                named_bar_sync(1, EPI_WARPS * 32);
+                for (int i = tid; i < 2 * p.bnt; i += EPI_WARPS * 32) {
+                    const int which = i >= p.bnt, col = which ? i - p.bnt : i;
+                    float tsum = 0.f;
+#pragma unroll
+                    for (int q = 0; q < EPI_WARPS; ++q) tsum += s_stat[(size_t)q * 512 + which * 256 + col];
+                    p.stats[((size_t)m_tile * 2 + which) * ctot + n_base + col] = tsum;
+                }
+                named_bar_sync(1, EPI_WARPS * 32);
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idesc = sv::make_idesc_tf32(BM, p.bnt, 0, 0);
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                sv::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+                sv::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * (p.tmem_cols >> 1);
+                for (int ks = 0; ks < p.kstages; ++ks) {
+                    sv::mbar_wait(&full_bar[stage], phase);
+                    sv::tc_fence_after();
+                    const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t a_lo = a_hi + A_TILE_BYTES;
+                    const uint32_t b_hi = a_lo + A_TILE_BYTES;
+                    const uint32_t b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const uint64_t da_hi = sv::make_smem_desc_sw128(a_hi + k4 * 32, 16, 1024);
+                        const uint64_t db_hi = sv::make_smem_desc_sw128(b_hi + k4 * 32, 16, 1024);
+                        if (p.passes == 3) {
+                            const uint64_t da_lo = sv::make_smem_desc_sw128(a_lo + k4 * 32, 16, 1024);
+                            const uint64_t db_lo = sv::make_smem_desc_sw128(b_lo + k4 * 32, 16, 1024);
+                            sv::umma_tf32(d_tmem, da_lo, db_hi, idesc, (ks | k4) ? 1u : 0u);
+                            sv::umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
+                            sv::umma_tf32(d_tmem, da_hi, db_hi, idesc, 1u);
+                        } else {
+                            sv::umma_tf32(d_tmem, da_hi, db_hi, idesc, (ks | k4) ? 1u : 0u);
+                        }
+                    }
+                    sv::umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                sv::umma_commit(&tfull_bar[acc]);  // accumulator complete
+            }
         }
     } else {
         // ------------------------------------------------------------------ B producer (one thread, TMA bulk)
         if (lane == 0) {
             const uint32_t bytes = (uint32_t)(p.passes == 3 ? 2 * b_tile_bytes : b_tile_bytes);
-            const unsigned char* wsrc = p.wpack + (size_t)ntile * p.kstages * 2 * b_tile_bytes;
             int stage = 0;
             uint32_t phase = 0;
-            for (int ks = 0; ks < p.kstages; ++ks) {
-                sv::mbar_wait(&empty_bar[stage], phase ^ 1);
-                sv::mbar_arrive_expect_tx(&full_bar[stage], bytes);
-                sv::bulk_g2s(smem + (size_t)stage * stage_bytes + 2 * A_TILE_BYTES, wsrc + (size_t)ks * 2 * b_tile_bytes,
-                             bytes, &full_bar[stage]);
-                if (++stage == p.stages) {
-                    stage = 0;
-                    phase ^= 1;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int ntile = tile % p.ntiles;
+                const unsigned char* wsrc = p.wpack + (size_t)ntile * p.kstages * 2 * b_tile_bytes;
+                for (int ks = 0; ks < p.kstages; ++ks) {
+                    sv::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    sv::mbar_arrive_expect_tx(&full_bar[stage], bytes);
+                    sv::bulk_g2s(smem + (size_t)stage * stage_bytes + 2 * A_TILE_BYTES,
+                                 wsrc + (size_t)ks * 2 * b_tile_bytes, bytes, &full_bar[stage]);
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
             }
         }
@@ -455,7 +524,7 @@ extern "C" int selavi_conv_gemm(const float* src, float* dst, const void* wpack,
     const int n_out = geom[19];
     if ((p.cs & 3) || (p.cd & 3) || p.cs <= 0 || p.cd <= 0) return selavi_fail(-1, "conv_gemm: channel strides must be multiples of 4");
     if (p.kt * p.kh * p.kw > MAX_TAPS) return selavi_fail(-1, "conv_gemm: too many taps");
-    if (p.td >= 1024 || p.hd >= 2048 || p.wd >= 1024) return selavi_fail(-1, "conv_gemm: spatial extent too large");
+    if (p.kt > 8 || p.kh > 8 || p.kw > 8) return selavi_fail(-1, "conv_gemm: kernel extent above 8 not supported");
     if ((p.st != 1 && p.st != 2) || (p.sh != 1 && p.sh != 2) || (p.sw != 1 && p.sw != 2)) return selavi_fail(-1, "conv_gemm: stride must be 1 or 2");
     if (passes != 1 && passes != 3) return selavi_fail(-1, "conv_gemm: passes must be 1 or 3");
     if ((pro_scale == nullptr) != (pro_shift == nullptr)) return selavi_fail(-1, "conv_gemm: prologue needs scale and shift");
@@ -465,25 +534,29 @@ extern "C" int selavi_conv_gemm(const float* src, float* dst, const void* wpack,
     pick_tiles(n_out, &p.bnt, &p.ntiles);
     // padded destination channels [n_out, cd) are written as exact zeros by the (zero) weight tile rows
     if (p.ntiles * p.bnt < p.cd) return selavi_fail(-1, "conv_gemm: cd exceeds the tiled channel range");
-    p.kchunks = p.kt * p.kh * p.kw * (p.cs >> 2);
-    p.kstages = (p.kchunks + 7) / 8;
+    p.kstages = (p.kt * p.kh * p.kw * (p.cs >> 2) + 7) / 8;
+    p.m_tiles = (p.M + BM - 1) / BM;
     p.pro_relu = pro_relu;
     p.accumulate = accumulate;
     p.passes = passes;
     uint32_t cols = 32;
-    while ((int)cols < p.bnt) cols <<= 1;
+    while ((int)cols < 2 * p.bnt) cols <<= 1;  // two accumulators (epilogue of tile i overlaps the MMAs of tile i+1)
     p.tmem_cols = cols;
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * p.bnt * 128;
-    const int tail_bytes = 8 * 8 * 2 + 8 + 8 + MAX_TAPS * 4 + LOADER_WARPS * 2 * 16 * 4 + 64;
+    const int tail_bytes = (2 * MAX_STAGES + 4) * 8 + 8 + 2 * MAX_TAPS * 4 + EPI_WARPS * 512 * 4 + 64;
     int stages = (227 * 1024 - 1024 - tail_bytes) / stage_bytes;
-    if (stages > 6) stages = 6;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages > p.kstages) stages = p.kstages < 1 ? 1 : p.kstages;
     if (stages < 2 && p.kstages > 1) return selavi_fail(-1, "conv_gemm: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + tail_bytes + 1024;
     SV_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                   "conv_gemm: cudaFuncSetAttribute");
-    dim3 grid((p.M + BM - 1) / BM, p.ntiles);
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int total_tiles = p.m_tiles * p.ntiles;
+    const int grid = total_tiles < sms ? total_tiles : sms;  // persistent: one CTA per SM
     conv_igemm_kernel<<<grid, CONV_THREADS, smem, (cudaStream_t)stream>>>(p);
     SV_CUDA_CHECK(cudaGetLastError(), "conv_gemm: launch");
     return 0;

@@ -47,4 +47,7 @@ class SGD(torch.optim.Optimizer):
                 _lib.check(lib.selavi_sgd_step(_lib.ptr(tbl[1]), len(ps), float(group["lr"]), float(group["momentum"]),
                                                float(group["weight_decay"]), 1 if first else 0, _lib.stream_ptr()),
                            "selavi_sgd_step")
+            # the kernel wrote the parameters behind autograd's back: bump their version counters so that
+            # version-keyed caches (the packed tensor-core weights in engine.py) see the update
+            torch.autograd.graph.increment_version(ps)
         return loss
