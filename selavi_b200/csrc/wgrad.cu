@@ -128,24 +128,31 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams 
         const int nb_blocks = (p.bnt >> 2);   // B channel groups
         int stage = 0;
         uint32_t phase = 0;
-        for (int ks = ks_begin; ks < ks_end; ++ks) {
+        // coordinates of this thread's first pixel of the current stage, advanced incrementally (32 pixels per stage)
+        int w0, h0, t0, n0;
+        {
+            const int mbase = ks_begin * WG_PIX + pg * 4;
+            w0 = mbase % p.wd;
+            const int t1 = mbase / p.wd;
+            h0 = t1 % p.hd;
+            const int t2 = t1 / p.hd;
+            t0 = t2 % p.td;
+            n0 = t2 / p.td;
+        }
+        int ks_g = ks_begin;   // stage index of the next gather
+        const bool hasb0 = cg < nb_blocks && n_off + cg * 4 < p.cd;
+        const bool hasb1 = cg + 32 < nb_blocks && n_off + (cg + 32) * 4 < p.cd;
+        struct WStage {
             float4 xa[4], xb0[4], xb1[4];
-            const int mbase = ks * WG_PIX + pg * 4;
-            int w_ = 0, h_ = 0, t_ = 0, n_ = 0;
-            if (mbase < p.M) {
-                w_ = mbase % p.wd;
-                const int t1 = mbase / p.wd;
-                h_ = t1 % p.hd;
-                const int t2 = t1 / p.hd;
-                t_ = t2 % p.td;
-                n_ = t2 / p.td;
-            }
+        };
+        auto gather = [&](WStage& s) {
+            const int mbase = ks_g * WG_PIX + pg * 4;
+            int w_ = w0, h_ = h0, t_ = t0, n_ = n0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int m = mbase + i;
-                xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                xb0[i] = xb1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m < p.M) {
+                s.xa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                s.xb0[i] = s.xb1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (mbase + i < p.M) {
                     const int a = t_ * p.st - p.pt + kt_;
                     const int b = h_ * p.sh - p.ph + kh_;
                     const int d = w_ * p.sw - p.pw + kw_;
@@ -165,14 +172,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams 
                                 x.w = fmaxf(x.w, 0.f);
                             }
                         }
-                        xa[i] = x;
+                        s.xa[i] = x;
                     }
-                    const float* zrow = p.dz + (size_t)m * p.cd + n_off;
-                    if (cg < nb_blocks && n_off + cg * 4 < p.cd) xb0[i] = __ldg(reinterpret_cast<const float4*>(zrow + cg * 4));
-                    if (cg + 32 < nb_blocks && n_off + (cg + 32) * 4 < p.cd)
-                        xb1[i] = __ldg(reinterpret_cast<const float4*>(zrow + (cg + 32) * 4));
-                    // next pixel
-                    if (++w_ == p.wd) {
+                    const float* zrow = p.dz + (size_t)(mbase + i) * p.cd + n_off;
+                    if (hasb0) s.xb0[i] = __ldg(reinterpret_cast<const float4*>(zrow + cg * 4));
+                    if (hasb1) s.xb1[i] = __ldg(reinterpret_cast<const float4*>(zrow + (cg + 32) * 4));
+                    if (++w_ == p.wd) {  // next pixel
                         w_ = 0;
                         if (++h_ == p.hd) {
                             h_ = 0;
@@ -184,24 +189,50 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams 
                     }
                 }
             }
-            transpose4(xa);
-            transpose4(xb0);
-            transpose4(xb1);
+            // advance the stage origin by WG_PIX pixels
+            ++ks_g;
+            w0 += WG_PIX;
+            while (w0 >= p.wd) {
+                w0 -= p.wd;
+                if (++h0 == p.hd) {
+                    h0 = 0;
+                    if (++t0 == p.td) {
+                        t0 = 0;
+                        ++n0;
+                    }
+                }
+            }
+        };
+        auto commit = [&](WStage& s) {
+            transpose4(s.xa);
+            if (hasb0) transpose4(s.xb0);
+            if (hasb1) transpose4(s.xb1);
             sv::mbar_wait(&empty_bar[stage], phase ^ 1);
             const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
             const uint32_t a_lo = a_hi + WG_A_BYTES;
             const uint32_t b_hi = a_lo + WG_A_BYTES;
             const uint32_t b_lo = b_hi + b_bytes;
             const bool with_lo = p.passes == 3;
-            store_rows4(a_hi, a_lo, cg * 4, pg, xa, with_lo);
-            if (cg < nb_blocks) store_rows4(b_hi, b_lo, cg * 4, pg, xb0, with_lo);
-            if (cg + 32 < nb_blocks) store_rows4(b_hi, b_lo, (cg + 32) * 4, pg, xb1, with_lo);
+            store_rows4(a_hi, a_lo, cg * 4, pg, s.xa, with_lo);
+            if (cg < nb_blocks) store_rows4(b_hi, b_lo, cg * 4, pg, s.xb0, with_lo);
+            if (cg + 32 < nb_blocks) store_rows4(b_hi, b_lo, (cg + 32) * 4, pg, s.xb1, with_lo);
             sv::fence_proxy_async();
             __syncwarp();
             if (lane == 0) sv::mbar_arrive(&full_bar[stage]);
             if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1;
+            }
+        };
+        // software pipeline: the loads of stage i+1 are in flight while stage i is transposed, split and stored
+        WStage sa, sb;
+        gather(sa);
+        for (int i = 0; i < nks; i += 2) {
+            if (i + 1 < nks) gather(sb);
+            commit(sa);
+            if (i + 1 < nks) {
+                if (i + 2 < nks) gather(sa);
+                commit(sb);
             }
         }
 
