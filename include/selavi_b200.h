@@ -75,7 +75,9 @@ int selavi_conv_gemm(const float* src, float* dst, const void* wpack, const int*
                      const float* pro_shift, int pro_relu, float* stats_partial, int accumulate, int passes,
                      void* stream);
 /* weight gradient: geom is the FORWARD geometry (mode 0), dz = gradient wrt the conv output [M, cd];
- * dW in the torch layout [co][ci_real][taps]; workspace of selavi_wgrad_workspace_bytes(co, taps, cs, M). */
+ * dW in the torch layout [co][ci_real][taps]; workspace of selavi_wgrad_workspace_bytes(co, taps, cs, M).
+ * passes: 3 = bf16x3 split / 1 = plain bf16 (operands stay MN-major, tcgen05.mma.kind::f16);
+ *         13 = tf32x3 / 11 = tf32 (K-major tiles, register-transposing loaders). */
 size_t selavi_wgrad_workspace_bytes(int co, int taps, int cs, long long M);
 int selavi_conv_wgrad(const float* src, const float* dz, float* dW, const int* geom, int ci_real,
                       const float* pro_scale, const float* pro_shift, int pro_relu, void* workspace, int accumulate,
@@ -175,12 +177,13 @@ int selavi_symm_free(void* ptr);
 int selavi_symm_memset(void* ptr, int value, size_t bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Diagnostics: issue n_mma tcgen05.mma.kind::tf32 instructions on host-provided raw shared-memory operand
+ * Diagnostics: issue n_mma tcgen05.mma instructions (kind 0 = tf32, 1 = f16/bf16) on host-provided raw shared-memory operand
  * images / descriptor bits and dump the 128 x N fp32 accumulator (tools/umma_probe.py).
  */
 int selavi_debug_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
                             unsigned long long adesc_base, unsigned long long bdesc_base, unsigned idesc, int n_mma,
-                            const unsigned* a_offs, const unsigned* b_offs, int N, float* out, void* stream);
+                            const unsigned* a_offs, const unsigned* b_offs, int N, int kind, float* out,
+                            void* stream);
 
 #ifdef __cplusplus
 }

@@ -76,7 +76,7 @@ SIGNATURES = {
     "selavi_mel_logfbank": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p, c_int, c_int, c_double, c_int,
                                     c_void_p, c_void_p]),
     "selavi_debug_umma_probe": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.c_ulonglong, ctypes.c_ulonglong,
-                                        ctypes.c_uint, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+                                        ctypes.c_uint, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "selavi_symm_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
     "selavi_symm_open": (c_int, [c_void_p, c_void_p]),
     "selavi_symm_close": (c_int, [c_void_p]),

@@ -12,7 +12,7 @@ namespace {
 __global__ void __launch_bounds__(160, 1)
 umma_probe_kernel(const uint4* a_img, int a_bytes, const uint4* b_img, int b_bytes, uint64_t adesc_base,
                   uint64_t bdesc_base, uint32_t idesc, int n_mma, const uint32_t* a_offs, const uint32_t* b_offs,
-                  int N, float* out) {
+                  int N, int kind, float* out) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* a_s = smem;
@@ -39,7 +39,8 @@ umma_probe_kernel(const uint4* a_img, int a_bytes, const uint4* b_img, int b_byt
         for (int i = 0; i < n_mma; ++i) {
             const uint64_t da = adesc_base | (uint64_t)(((sv::smem_u32(a_s) + a_offs[i]) & 0x3FFFFu) >> 4);
             const uint64_t db = bdesc_base | (uint64_t)(((sv::smem_u32(b_s) + b_offs[i]) & 0x3FFFFu) >> 4);
-            sv::umma_tf32(tmem_base, da, db, idesc, i ? 1u : 0u);
+            if (kind == 0) sv::umma_tf32(tmem_base, da, db, idesc, i ? 1u : 0u);
+            else sv::umma_f16(tmem_base, da, db, idesc, i ? 1u : 0u);
         }
         sv::umma_commit(&bar);
     }
@@ -64,8 +65,8 @@ umma_probe_kernel(const uint4* a_img, int a_bytes, const uint4* b_img, int b_byt
 
 extern "C" int selavi_debug_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
                                        unsigned long long adesc_base, unsigned long long bdesc_base, unsigned idesc,
-                                       int n_mma, const unsigned* a_offs, const unsigned* b_offs, int N, float* out,
-                                       void* stream) {
+                                       int n_mma, const unsigned* a_offs, const unsigned* b_offs, int N, int kind,
+                                       float* out, void* stream) {
     if (!a_img || !b_img || !a_offs || !b_offs || !out || (a_bytes & 15) || (b_bytes & 15) || N % 8 || N > 256)
         return selavi_fail(-1, "umma_probe: bad arguments");
     const size_t smem = (size_t)((a_bytes + 1023) & ~1023) + ((b_bytes + 1023) & ~1023) + 2048;
@@ -74,7 +75,7 @@ extern "C" int selavi_debug_umma_probe(const void* a_img, int a_bytes, const voi
                   "umma_probe: attr");
     umma_probe_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(a_img), a_bytes, reinterpret_cast<const uint4*>(b_img), b_bytes, adesc_base,
-        bdesc_base, idesc, n_mma, a_offs, b_offs, N, out);
+        bdesc_base, idesc, n_mma, a_offs, b_offs, N, kind, out);
     SV_CUDA_CHECK(cudaGetLastError(), "umma_probe: launch");
     return 0;
 }

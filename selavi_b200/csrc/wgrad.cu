@@ -11,6 +11,7 @@
 // BN+ReLU prologue of the previous layer and the tf32 hi/lo split are done in registers like in conv.cu.  The pixel range is split
 // over CTAs (split-K); partial tiles go to a [slices][taps*cs][co] buffer that wgrad_reduce sums in a fixed
 // order and scatters into the torch weight layout (deterministic, no atomics).
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 #include "../../include/selavi_b200.h"
@@ -300,6 +301,294 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// bf16x3 variant: both operands stay MN-major (channels contiguous, exactly as they lie in HBM) — supported by
+// tcgen05.mma.kind::f16 (probed: profiles/r01_umma_probe_bf16.txt), so the loaders neither transpose nor gather
+// more than 32 contiguous bytes per thread; x = hi + lo with hi = bf16(x), lo = bf16(x - hi) and three MMAs
+// (lo*hi + hi*lo + hi*hi, fp32 accumulate) give ~2^-17 relative operand error, twice the tf32 MMA rate and half
+// the shared-memory bytes.  Tile layout: SWIZZLE_128B MN-major atoms [k-group of 8 pixels][chunk of 64 channels].
+__device__ __forceinline__ void split_bf16x8(const float4& p, const float4& q, uint4& hi, uint4& lo) {
+    const float x[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 hb = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+        const __nv_bfloat162 lb = __floats2bfloat162_rn(x[2 * i] - __low2float(hb), x[2 * i + 1] - __high2float(hb));
+        h[i] = *reinterpret_cast<const uint32_t*>(&hb);
+        l[i] = *reinterpret_cast<const uint32_t*>(&lb);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+constexpr int WB_LOADER_WARPS = 8;
+constexpr int WB_MMA_WARP = WB_LOADER_WARPS;
+constexpr int WB_THREADS = (WB_LOADER_WARPS + 1) * 32;
+constexpr int WB_LTHREADS = WB_LOADER_WARPS * 32;
+constexpr int WB_A_BYTES = 4 * 2 * 1024;   // 4 k-groups x 2 chunks of 64 channels
+
+__global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int nchb = (p.bnt + 63) >> 6;              // 64-channel chunks of the B tile
+    const int b_bytes = 4 * nchb * 1024;
+    const int stage_bytes = 2 * WB_A_BYTES + 2 * b_bytes;   // A_hi | A_lo | B_hi | B_lo
+    unsigned char* tail = smem + (size_t)p.stages * stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* empty_bar = full_bar + 8;
+    uint64_t* accum_bar = empty_bar + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int mt = blockIdx.x % p.mtiles;
+    const int ntile = blockIdx.x / p.mtiles;
+    const int slice = blockIdx.y;
+    const int ks_begin = slice * p.kstages_per_slice;
+    int ks_end = ks_begin + p.kstages_per_slice;
+    if (ks_end > p.total_kstages) ks_end = p.total_kstages;
+    const int nks = ks_end - ks_begin;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            sv::mbar_init(&full_bar[s], WB_LOADER_WARPS);
+            sv::mbar_init(&empty_bar[s], 1);
+        }
+        sv::mbar_init(accum_bar, 1);
+        sv::fence_barrier_init();
+    }
+    if (warp == WB_MMA_WARP) {
+        sv::tmem_alloc(tmem_slot, p.tmem_cols);
+        sv::tmem_relinquish();
+    }
+    sv::tc_fence_before();
+    __syncthreads();
+    sv::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_off = ntile * p.bnt;
+
+    if (warp < WB_LOADER_WARPS) {
+        const int C4 = p.cs >> 2;
+        const int taps = p.kt * p.kh * p.kw;
+        const bool pro = p.pro_scale != nullptr;
+        // ---- A units (pixel, 8-row group): u = tid + 256*j, px = u >> 4, g8 = u & 15; the two 4-channel halves of a
+        //      unit are independent flattened K chunks (tap, c4) — fixed per thread for the whole kernel
+        const int g8a = tid & 15;
+        int a_kt[2], a_kh[2], a_kw[2], a_c4[2];
+        bool a_valid[2];
+        float4 a_sc[2], a_sf[2];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int Q = (mt * 16 + g8a) * 2 + hf;
+            const int tap = Q / C4;
+            a_c4[hf] = Q % C4;
+            a_valid[hf] = tap < taps;
+            a_kw[hf] = tap % p.kw;
+            a_kh[hf] = (tap / p.kw) % p.kh;
+            a_kt[hf] = tap / (p.kw * p.kh);
+            a_sc[hf] = make_float4(1.f, 1.f, 1.f, 1.f);
+            a_sf[hf] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pro && a_valid[hf]) {
+                a_sc[hf] = __ldg(reinterpret_cast<const float4*>(p.pro_scale + a_c4[hf] * 4));
+                a_sf[hf] = __ldg(reinterpret_cast<const float4*>(p.pro_shift + a_c4[hf] * 4));
+            }
+        }
+        // coordinates of this thread's two A pixels (px = tid>>4 and 16 + tid>>4), advanced by 32 pixels per stage
+        int cw[2], ch_[2], ct[2], cn[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int m = ks_begin * WG_PIX + (tid >> 4) + 16 * j;
+            cw[j] = m % p.wd;
+            const int t1 = m / p.wd;
+            ch_[j] = t1 % p.hd;
+            const int t2 = t1 / p.hd;
+            ct[j] = t2 % p.td;
+            cn[j] = t2 / p.td;
+        }
+        // ---- B units (pixel, 8-channel group): u = tid + 256*j, px = u / upp, g8 = u % upp
+        const int upp = (p.bnt + 7) >> 3;
+        int b_px[4], b_g8[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int u = tid + WB_LTHREADS * j;
+            b_px[j] = u / upp;
+            b_g8[j] = u % upp;
+            if (b_px[j] >= WG_PIX) b_px[j] = -1;
+        }
+        int ks_g = ks_begin;
+        struct BStage {
+            float4 a[2][2];   // [pixel j][half]
+            float4 b[4][2];   // [unit j][half]
+        };
+        auto gather = [&](BStage& s) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int m = ks_g * WG_PIX + (tid >> 4) + 16 * j;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (m < p.M && a_valid[hf]) {
+                        const int a = ct[j] * p.st - p.pt + a_kt[hf];
+                        const int b = ch_[j] * p.sh - p.ph + a_kh[hf];
+                        const int d = cw[j] * p.sw - p.pw + a_kw[hf];
+                        if ((a >= 0) & (a < p.ts) & (b >= 0) & (b < p.hs) & (d >= 0) & (d < p.ws)) {
+                            const size_t pix = (size_t)((cn[j] * p.ts + a) * p.hs + b) * p.ws + d;
+                            x = __ldg(reinterpret_cast<const float4*>(p.src + pix * p.cs + a_c4[hf] * 4));
+                            if (pro) {
+                                x.x = fmaf(x.x, a_sc[hf].x, a_sf[hf].x);
+                                x.y = fmaf(x.y, a_sc[hf].y, a_sf[hf].y);
+                                x.z = fmaf(x.z, a_sc[hf].z, a_sf[hf].z);
+                                x.w = fmaf(x.w, a_sc[hf].w, a_sf[hf].w);
+                                if (p.pro_relu) {
+                                    x.x = fmaxf(x.x, 0.f);
+                                    x.y = fmaxf(x.y, 0.f);
+                                    x.z = fmaxf(x.z, 0.f);
+                                    x.w = fmaxf(x.w, 0.f);
+                                }
+                            }
+                        }
+                    }
+                    s.a[j][hf] = x;
+                }
+                // advance this pixel by WG_PIX for the next stage
+                cw[j] += WG_PIX;
+                while (cw[j] >= p.wd) {
+                    cw[j] -= p.wd;
+                    if (++ch_[j] == p.hd) {
+                        ch_[j] = 0;
+                        if (++ct[j] == p.td) {
+                            ct[j] = 0;
+                            ++cn[j];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s.b[j][0] = s.b[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (b_px[j] >= 0) {
+                    const int m = ks_g * WG_PIX + b_px[j];
+                    const int c0 = n_off + b_g8[j] * 8;
+                    if (m < p.M) {
+                        const float* zp = p.dz + (size_t)m * p.cd + c0;
+                        if (c0 < p.cd) s.b[j][0] = __ldg(reinterpret_cast<const float4*>(zp));
+                        if (c0 + 4 < p.cd) s.b[j][1] = __ldg(reinterpret_cast<const float4*>(zp + 4));
+                    }
+                }
+            }
+            ++ks_g;
+        };
+        int stage = 0;
+        uint32_t phase = 0;
+        auto commit = [&](const BStage& s) {
+            sv::mbar_wait(&empty_bar[stage], phase ^ 1);
+            const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t a_lo = a_hi + WB_A_BYTES;
+            const uint32_t b_hi = a_lo + WB_A_BYTES;
+            const uint32_t b_lo = b_hi + b_bytes;
+            const bool with_lo = p.passes == 3;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int px = (tid >> 4) + 16 * j;
+                uint4 hi, lo;
+                split_bf16x8(s.a[j][0], s.a[j][1], hi, lo);
+                const uint32_t off = (uint32_t)(((px >> 3) * 2 + (g8a >> 3)) * 1024 + (px & 7) * 128 + (((g8a & 7) ^ (px & 7)) << 4));
+                wg_st4(a_hi + off, hi.x, hi.y, hi.z, hi.w);
+                if (with_lo) wg_st4(a_lo + off, lo.x, lo.y, lo.z, lo.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (b_px[j] >= 0) {
+                    const int px = b_px[j], g8 = b_g8[j];
+                    uint4 hi, lo;
+                    split_bf16x8(s.b[j][0], s.b[j][1], hi, lo);
+                    const uint32_t off = (uint32_t)(((px >> 3) * nchb + (g8 >> 3)) * 1024 + (px & 7) * 128 + (((g8 & 7) ^ (px & 7)) << 4));
+                    wg_st4(b_hi + off, hi.x, hi.y, hi.z, hi.w);
+                    if (with_lo) wg_st4(b_lo + off, lo.x, lo.y, lo.z, lo.w);
+                }
+            }
+            sv::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) sv::mbar_arrive(&full_bar[stage]);
+            if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+            }
+        };
+        BStage sa, sb;
+        gather(sa);
+        for (int i = 0; i < nks; i += 2) {
+            if (i + 1 < nks) gather(sb);
+            commit(sa);
+            if (i + 1 < nks) {
+                if (i + 2 < nks) gather(sa);
+                commit(sb);
+            }
+        }
+        // ---- epilogue: TMEM -> partial[slice][mt*128 + row][ntile*bnt + col]
+        sv::mbar_wait(accum_bar, 0);
+        sv::tc_fence_after();
+        const int quad = warp & 3, half = warp >> 2;
+        const int units = p.bnt >> 4;
+        const int u_begin = half == 0 ? 0 : (units + 1) / 2;
+        const int u_end = half == 0 ? (units + 1) / 2 : units;
+        const int row = quad * 32 + lane;
+        const int ntot = p.ntiles * p.bnt;
+        float* out_row = p.partial + ((size_t)slice * (p.mtiles * 128) + mt * 128 + row) * ntot + n_off;
+        for (int u = u_begin; u < u_end; ++u) {
+            uint32_t acc[16];
+            sv::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(u * 16), acc);
+            sv::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                *reinterpret_cast<float4*>(out_row + u * 16 + i) =
+                    make_float4(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]),
+                                __uint_as_float(acc[i + 3]));
+            }
+        }
+        sv::tc_fence_before();
+    } else {
+        if (lane == 0) {
+            const uint32_t idesc = sv::make_idesc_f16(128, p.bnt, 1, 1, 1, 1);  // bf16 x bf16, both MN-major
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t a_sbo = 2 * 1024, b_sbo = (uint32_t)(nchb * 1024);
+            for (int i = 0; i < nks; ++i) {
+                sv::mbar_wait(&full_bar[stage], phase);
+                sv::tc_fence_after();
+                const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t a_lo = a_hi + WB_A_BYTES;
+                const uint32_t b_hi = a_lo + WB_A_BYTES;
+                const uint32_t b_lo = b_hi + b_bytes;
+#pragma unroll
+                for (int k16 = 0; k16 < 2; ++k16) {   // UMMA_K = 16 pixels = 2 k-groups of 8
+                    const uint64_t da_hi = sv::make_smem_desc(a_hi + k16 * 2 * a_sbo, 1024, a_sbo, 2);
+                    const uint64_t db_hi = sv::make_smem_desc(b_hi + k16 * 2 * b_sbo, 1024, b_sbo, 2);
+                    if (p.passes == 3) {
+                        const uint64_t da_lo = sv::make_smem_desc(a_lo + k16 * 2 * a_sbo, 1024, a_sbo, 2);
+                        const uint64_t db_lo = sv::make_smem_desc(b_lo + k16 * 2 * b_sbo, 1024, b_sbo, 2);
+                        sv::umma_f16(tmem_base, da_lo, db_hi, idesc, (i | k16) ? 1u : 0u);
+                        sv::umma_f16(tmem_base, da_hi, db_lo, idesc, 1u);
+                        sv::umma_f16(tmem_base, da_hi, db_hi, idesc, 1u);
+                    } else {
+                        sv::umma_f16(tmem_base, da_hi, db_hi, idesc, (i | k16) ? 1u : 0u);
+                    }
+                }
+                sv::umma_commit(&empty_bar[stage]);
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            sv::umma_commit(accum_bar);
+        }
+    }
+    __syncthreads();
+    if (warp == WB_MMA_WARP) {
+        sv::tc_fence_after();
+        sv::tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
 // dW[co][ci][tap] (+)= sum_s partial[s][tap*cs + ci][co]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int slices, int mg_pad, int ntot, int co, int ci,
                                     int taps, int cs, float* __restrict__ dW, int accumulate) {
@@ -337,7 +626,8 @@ WgPlan wg_plan(int co, int taps, int cs, long long M) {
     pl.mtiles = (taps * cs + 127) / 128;
     pl.total_kstages = (int)((M + WG_PIX - 1) / WG_PIX);
     const int tiles = pl.mtiles * pl.ntiles;
-    int slices = (148 * 3 + tiles - 1) / tiles;  // about 3 waves of CTAs
+    int slices = (148 * 3) / tiles;  // at most 3 full waves of CTAs (no tail wave)
+    if (slices < 1) slices = 1;
     if (slices > pl.total_kstages) slices = pl.total_kstages;
     if (slices > 256) slices = 256;
     if (slices < 1) slices = 1;
@@ -371,7 +661,8 @@ extern "C" int selavi_conv_wgrad(const float* src, const float* dz, float* dW, c
     p.pt = geom[16]; p.ph = geom[17]; p.pw = geom[18];
     const int co = geom[19];
     if ((p.cs & 3) || (p.cd & 3)) return selavi_fail(-1, "conv_wgrad: channel strides must be multiples of 4");
-    if (passes != 1 && passes != 3) return selavi_fail(-1, "conv_wgrad: passes must be 1 or 3");
+    // passes: 3 = bf16x3 / 1 = bf16 (MN-major kind::f16 kernel); 13 = tf32x3 / 11 = tf32 (K-major transposing kernel)
+    if (passes != 1 && passes != 3 && passes != 11 && passes != 13) return selavi_fail(-1, "conv_wgrad: passes must be 1, 3, 11 or 13");
     if ((pro_scale == nullptr) != (pro_shift == nullptr)) return selavi_fail(-1, "conv_wgrad: prologue needs scale and shift");
     const long long M = (long long)p.nb * p.td * p.hd * p.wd;
     if (M <= 0 || M > 0x7fffffffLL) return selavi_fail(-1, "conv_wgrad: bad pixel count");
@@ -381,21 +672,28 @@ extern "C" int selavi_conv_wgrad(const float* src, const float* dz, float* dW, c
     p.mtiles = pl.mtiles; p.bnt = pl.bnt; p.ntiles = pl.ntiles; p.natom = pl.natom;
     p.total_kstages = pl.total_kstages; p.kstages_per_slice = pl.kstages_per_slice;
     p.pro_relu = pro_relu;
-    p.passes = passes;
+    const bool bf16 = passes < 10;
+    p.passes = bf16 ? passes : passes - 10;
     uint32_t cols = 32;
     while ((int)cols < p.bnt) cols <<= 1;
     p.tmem_cols = cols;
-    const int stage_bytes = 2 * WG_A_BYTES + 2 * p.bnt * 128;
+    const int stage_bytes = bf16 ? 2 * WB_A_BYTES + 2 * 4 * ((p.bnt + 63) / 64) * 1024 : 2 * WG_A_BYTES + 2 * p.bnt * 128;
     const int tail_bytes = 8 * 8 * 2 + 8 + 8 + 64;
     int stages = (227 * 1024 - 1024 - tail_bytes) / stage_bytes;
     if (stages > 6) stages = 6;
     if (stages < 2) return selavi_fail(-1, "conv_wgrad: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + tail_bytes + 1024;
-    SV_CUDA_CHECK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                  "conv_wgrad: cudaFuncSetAttribute");
     dim3 grid(pl.mtiles * pl.ntiles, pl.slices);
-    wgrad_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(p);
+    if (bf16) {
+        SV_CUDA_CHECK(cudaFuncSetAttribute(wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                      "conv_wgrad: cudaFuncSetAttribute");
+        wgrad_bf16_kernel<<<grid, WB_THREADS, smem, (cudaStream_t)stream>>>(p);
+    } else {
+        SV_CUDA_CHECK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                      "conv_wgrad: cudaFuncSetAttribute");
+        wgrad_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(p);
+    }
     SV_CUDA_CHECK(cudaGetLastError(), "conv_wgrad: launch");
     const size_t total = (size_t)co * ci_real * taps;
     int blocks = (int)((total + 255) / 256);

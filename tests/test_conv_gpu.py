@@ -93,8 +93,10 @@ def test_conv_dgrad(cuda_device, name):
     assert _rel(dx2, 2 * dx) < 1e-6
 
 
+# passes 3 = bf16x3 MN-major kernel (default), 13 = tf32x3 K-major transposing kernel
+@pytest.mark.parametrize("passes", [3, 13])
 @pytest.mark.parametrize("name", sorted(LAYERS))
-def test_conv_wgrad(cuda_device, name):
+def test_conv_wgrad(cuda_device, name, passes):
     from selavi_b200 import ops
     x, w, geom, (s, p) = _mk(name, cuda_device)
     wd = w.double().requires_grad_(True)
@@ -102,7 +104,7 @@ def test_conv_wgrad(cuda_device, name):
     dz = torch.randn(ref_y.shape, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(9))
     ref_dw, = torch.autograd.grad(ref_y, wd, dz.double())
     dw = torch.empty_like(w)
-    ops.conv_wgrad(ops.to_channels_last(x), ops.to_channels_last(dz), geom, dw)
+    ops.conv_wgrad(ops.to_channels_last(x), ops.to_channels_last(dz), geom, dw, passes=passes)
     err = _rel(dw, ref_dw)
-    print(f"{name} wgrad rel={err:.3e}")
+    print(f"{name} wgrad passes={passes} rel={err:.3e}")
     assert err < 5e-5

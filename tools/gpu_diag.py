@@ -12,7 +12,6 @@ CHECKS = [
     ("conv_fwd_all", "tests/test_conv_gpu.py::test_conv_forward"),
     ("conv_fwd_pro", "tests/test_conv_gpu.py::test_conv_forward_fused_bn_relu_prologue_and_stats"),
     ("conv_dgrad", "tests/test_conv_gpu.py::test_conv_dgrad"),
-    ("conv_wgrad_gemm", "tests/test_conv_gpu.py::test_conv_wgrad[gemm_1x1x1]"),
     ("conv_wgrad", "tests/test_conv_gpu.py::test_conv_wgrad"),
     ("heads", "tests/test_model_gpu.py::test_heads_linear_and_dropout_paths"),
     ("ce", "tests/test_model_gpu.py::test_ce_loss_matches_torch"),

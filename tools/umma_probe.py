@@ -94,7 +94,7 @@ def run(a_img, a_offs, a_bits, b_img, b_offs, b_bits, idesc_v, N, dev):
     out = torch.zeros(128, N, dtype=torch.float32, device=dev)
     pad = lambda t: (t.numel() * 4 + 15) // 16 * 16
     code = lib.selavi_debug_umma_probe(_lib.ptr(a), pad(a), _lib.ptr(b), pad(b), ctypes.c_ulonglong(a_bits),
-                                       ctypes.c_ulonglong(b_bits), idesc_v, len(a_offs), _lib.ptr(ao), _lib.ptr(bo), N,
+                                       ctypes.c_ulonglong(b_bits), idesc_v, len(a_offs), _lib.ptr(ao), _lib.ptr(bo), N, 0,
                                        _lib.ptr(out), _lib.stream_ptr())
     _lib.check(code, "probe")
     torch.cuda.synchronize()
