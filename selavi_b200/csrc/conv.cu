@@ -30,7 +30,9 @@ namespace {
 constexpr int BM = 128;            // pixels per tile (UMMA M)
 constexpr int BK = 32;             // fp32 elements per K stage (one 128B swizzle row)
 constexpr int EPI_WARPS = 4;       // warps 0..3  : epilogue (TMEM lane quadrant = warp id)
-constexpr int LOADER_WARPS = 8;    // warps 4..11 : A-operand gather
+constexpr int LOADER_WARPS = 16;   // warps 4..19 : A-operand gather (4 per scheduler: the gather streams are latency-bound)
+constexpr int ROWS_PER = 1024 / (LOADER_WARPS * 32);   // tile rows per loader thread
+constexpr int ROW_STEP = LOADER_WARPS * 4;             // row distance between a thread's rows
 constexpr int MMA_WARP = EPI_WARPS + LOADER_WARPS;
 constexpr int BPROD_WARP = MMA_WARP + 1;
 constexpr int CONV_THREADS = (BPROD_WARP + 1) * 32;
@@ -68,7 +70,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // One gathered K stage of a loader thread: 4 rows x one 16-byte chunk, plus the prologue affine of that chunk.
 struct AStage {
-    float4 v[4];
+    float4 v[ROWS_PER];
     float4 sc, sf;
     uint32_t okmask;  // bit j: row j valid for this tap (prologue applies, otherwise exact zero)
 };
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
         // ------------------------------------------------------------------ A loaders (256 threads)
         const int ltid = tid - EPI_WARPS * 32;
         const int c = ltid & 7;    // 16-byte chunk within the 128B K row
-        const int r0 = ltid >> 3;  // rows r0 + 32*j
+        const int r0 = ltid >> 3;  // rows r0 + ROW_STEP*j
         const int C4 = p.cs >> 2;
         const uint32_t sw_off = (uint32_t)((c ^ (r0 & 7)) << 4);
         const bool pro = p.pro_scale != nullptr;
@@ -138,11 +140,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m0 = (tile / p.ntiles) * BM;
             // per-row gather base (pixel index of tap 0) and per-dimension tap validity bits
-            int pb[4];
-            uint32_t vm[4];
+            int pb[ROWS_PER];
+            uint32_t vm[ROWS_PER];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int m = m0 + r0 + 32 * j;
+            for (int j = 0; j < ROWS_PER; ++j) {
+                const int m = m0 + r0 + ROW_STEP * j;
                 pb[j] = 0;
                 vm[j] = 0;
                 if (m < p.M) {
@@ -200,13 +202,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
                 a.sc = make_float4(1.f, 1.f, 1.f, 1.f);
                 a.sf = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) a.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < ROWS_PER; ++j) a.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (tap < taps) {
                     const int pk = tap_dt[tap];
                     const int off = tap_off[tap];
                     const int s_t = pk & 255, s_h = 8 + ((pk >> 8) & 255), s_w = 16 + ((pk >> 16) & 255);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < ROWS_PER; ++j) {
                         const uint32_t m_ = vm[j];
                         if ((m_ >> 31) & (m_ >> s_t) & (m_ >> s_h) & (m_ >> s_w) & 1u) {
                             a.v[j] = __ldg(reinterpret_cast<const float4*>(p.src + (size_t)(pb[j] + off) * p.cs + c4 * 4));
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
                 const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint32_t a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < ROWS_PER; ++j) {
                     float4 x = a.v[j];
                     if (pro && ((a.okmask >> j) & 1u)) {
                         x.x = fmaf(x.x, a.sc.x, a.sf.x);
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
                             x.w = fmaxf(x.w, 0.f);
                         }
                     }
-                    const uint32_t row_off = (uint32_t)((r0 + 32 * j) * 128) + sw_off;
+                    const uint32_t row_off = (uint32_t)((r0 + ROW_STEP * j) * 128) + sw_off;
                     const uint32_t h0 = tf32_hi(x.x), h1 = tf32_hi(x.y), h2 = tf32_hi(x.z), h3 = tf32_hi(x.w);
                     st_shared_v4(a_hi + row_off, h0, h1, h2, h3);
                     if (p.passes == 3) {

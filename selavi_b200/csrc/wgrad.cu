@@ -321,7 +321,9 @@ __device__ __forceinline__ void split_bf16x8(const float4& p, const float4& q, u
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-constexpr int WB_LOADER_WARPS = 8;
+constexpr int WB_LOADER_WARPS = 16;             // 4 per scheduler: the gather/convert streams are latency-bound
+constexpr int WB_A_PER = 512 / (WB_LOADER_WARPS * 32);   // A units (pixel, 8 channels) per thread and stage
+constexpr int WB_B_PER = 1024 / (WB_LOADER_WARPS * 32);  // B units per thread and stage
 constexpr int WB_MMA_WARP = WB_LOADER_WARPS;
 constexpr int WB_THREADS = (WB_LOADER_WARPS + 1) * 32;
 constexpr int WB_LTHREADS = WB_LOADER_WARPS * 32;
@@ -393,10 +395,10 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradPa
             }
         }
         // coordinates of this thread's two A pixels (px = tid>>4 and 16 + tid>>4), advanced by 32 pixels per stage
-        int cw[2], ch_[2], ct[2], cn[2];
+        int cw[WB_A_PER], ch_[WB_A_PER], ct[WB_A_PER], cn[WB_A_PER];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int m = ks_begin * WG_PIX + (tid >> 4) + 16 * j;
+        for (int j = 0; j < WB_A_PER; ++j) {
+            const int m = ks_begin * WG_PIX + (tid >> 4) + (WB_LTHREADS >> 4) * j;
             cw[j] = m % p.wd;
             const int t1 = m / p.wd;
             ch_[j] = t1 % p.hd;
@@ -406,9 +408,9 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradPa
         }
         // ---- B units (pixel, 8-channel group): u = tid + 256*j, px = u / upp, g8 = u % upp
         const int upp = (p.bnt + 7) >> 3;
-        int b_px[4], b_g8[4];
+        int b_px[WB_B_PER], b_g8[WB_B_PER];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < WB_B_PER; ++j) {
             const int u = tid + WB_LTHREADS * j;
             b_px[j] = u / upp;
             b_g8[j] = u % upp;
@@ -416,13 +418,13 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradPa
         }
         int ks_g = ks_begin;
         struct BStage {
-            float4 a[2][2];   // [pixel j][half]
-            float4 b[4][2];   // [unit j][half]
+            float4 a[WB_A_PER][2];   // [pixel j][half]
+            float4 b[WB_B_PER][2];   // [unit j][half]
         };
         auto gather = [&](BStage& s) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int m = ks_g * WG_PIX + (tid >> 4) + 16 * j;
+            for (int j = 0; j < WB_A_PER; ++j) {
+                const int m = ks_g * WG_PIX + (tid >> 4) + (WB_LTHREADS >> 4) * j;
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradPa
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < WB_B_PER; ++j) {
                 s.b[j][0] = s.b[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (b_px[j] >= 0) {
                     const int m = ks_g * WG_PIX + b_px[j];
@@ -487,8 +489,8 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradPa
             const uint32_t b_lo = b_hi + b_bytes;
             const bool with_lo = p.passes == 3;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int px = (tid >> 4) + 16 * j;
+            for (int j = 0; j < WB_A_PER; ++j) {
+                const int px = (tid >> 4) + (WB_LTHREADS >> 4) * j;
                 uint4 hi, lo;
                 split_bf16x8(s.a[j][0], s.a[j][1], hi, lo);
                 const uint32_t off = (uint32_t)(((px >> 3) * 2 + (g8a >> 3)) * 1024 + (px & 7) * 128 + (((g8a & 7) ^ (px & 7)) << 4));
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradPa
                 if (with_lo) wg_st4(a_lo + off, lo.x, lo.y, lo.z, lo.w);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < WB_B_PER; ++j) {
                 if (b_px[j] >= 0) {
                     const int px = b_px[j], g8 = b_g8[j];
                     uint4 hi, lo;
@@ -527,10 +529,11 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradPa
         // ---- epilogue: TMEM -> partial[slice][mt*128 + row][ntile*bnt + col]
         sv::mbar_wait(accum_bar, 0);
         sv::tc_fence_after();
-        const int quad = warp & 3, half = warp >> 2;
+        const int quad = warp & 3, part = warp >> 2;            // WB_LOADER_WARPS / 4 column parts
         const int units = p.bnt >> 4;
-        const int u_begin = half == 0 ? 0 : (units + 1) / 2;
-        const int u_end = half == 0 ? (units + 1) / 2 : units;
+        constexpr int PARTS = WB_LOADER_WARPS / 4;
+        const int u_begin = (units * part) / PARTS;
+        const int u_end = (units * (part + 1)) / PARTS;
         const int row = quad * 32 + lane;
         const int ntot = p.ntiles * p.bnt;
         float* out_row = p.partial + ((size_t)slice * (p.mtiles * 128) + mt * 128 + row) * ntot + n_off;
