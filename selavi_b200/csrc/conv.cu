@@ -30,7 +30,7 @@ namespace {
 constexpr int BM = 128;            // pixels per tile (UMMA M)
 constexpr int BK = 32;             // fp32 elements per K stage (one 128B swizzle row)
 constexpr int EPI_WARPS = 4;       // warps 0..3  : epilogue (TMEM lane quadrant = warp id)
-constexpr int LOADER_WARPS = 16;   // warps 4..19 : A-operand gather (4 per scheduler: the gather streams are latency-bound)
+constexpr int LOADER_WARPS = 8;    // warps 4..19 : A-operand gather (4 per scheduler: the gather streams are latency-bound)
 constexpr int ROWS_PER = 1024 / (LOADER_WARPS * 32);   // tile rows per loader thread
 constexpr int ROW_STEP = LOADER_WARPS * 4;             // row distance between a thread's rows
 constexpr int MMA_WARP = EPI_WARPS + LOADER_WARPS;

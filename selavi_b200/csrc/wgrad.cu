@@ -321,7 +321,7 @@ __device__ __forceinline__ void split_bf16x8(const float4& p, const float4& q, u
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-constexpr int WB_LOADER_WARPS = 16;             // 4 per scheduler: the gather/convert streams are latency-bound
+constexpr int WB_LOADER_WARPS = 8;              // 4 per scheduler: the gather/convert streams are latency-bound
 constexpr int WB_A_PER = 512 / (WB_LOADER_WARPS * 32);   // A units (pixel, 8 channels) per thread and stage
 constexpr int WB_B_PER = 1024 / (WB_LOADER_WARPS * 32);  // B units per thread and stage
 constexpr int WB_MMA_WARP = WB_LOADER_WARPS;
