@@ -55,7 +55,7 @@ int selavi_sk_solve(double* PS, long long n_local, long long n_global, int K, do
  * calls behind torchvision Conv2Plus1D / BasicBlock / stems / downsamples, tv:video/resnet.py:45-61,184-195,
  * 276-281 and tv:resnet.py:59-105, built by model.py:93-121).
  *
- * Activations: channels-last fp32 [N,T,H,W,Cs], Cs = channels padded to a multiple of 4 (pad channels zero).
+ * Activations: channels-last fp32 [N,T,H,W,Cs], Cs = channels padded to a multiple of 8 (pad channels zero).
  * geom[20] = {mode, nb, ts,hs,ws,cs, td,hd,wd,cd, kt,kh,kw, st,sh,sw, pt,ph,pw, n_out}
  *   mode 0 (forward):  src = conv input, dst = conv output; dst pixel (t,h,w) reads src (t*st-pt+kt, ...).
  *   mode 1 (dgrad):    src = gradient wrt conv output, dst = gradient wrt conv input; st.. and pt.. are the FORWARD
@@ -75,10 +75,10 @@ int selavi_conv_gemm(const float* src, float* dst, const void* wpack, const int*
                      const float* pro_shift, int pro_relu, float* stats_partial, int accumulate, int passes,
                      void* stream);
 /* weight gradient: geom is the FORWARD geometry (mode 0), dz = gradient wrt the conv output [M, cd];
- * dW in the torch layout [co][ci_real][taps]; workspace of selavi_wgrad_workspace_bytes(co, taps, cs, M).
+ * dW in the torch layout [co][ci_real][taps]; workspace of selavi_wgrad_workspace_bytes(geom).
  * passes: 3 = bf16x3 split / 1 = plain bf16 (operands stay MN-major, tcgen05.mma.kind::f16);
  *         13 = tf32x3 / 11 = tf32 (K-major tiles, register-transposing loaders). */
-size_t selavi_wgrad_workspace_bytes(int co, int taps, int cs, long long M);
+size_t selavi_wgrad_workspace_bytes(const int* geom);
 int selavi_conv_wgrad(const float* src, const float* dz, float* dW, const int* geom, int ci_real,
                       const float* pro_scale, const float* pro_shift, int pro_relu, void* workspace, int accumulate,
                       int passes, void* stream);

@@ -33,7 +33,7 @@ SIGNATURES = {
     "selavi_conv_pack_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "selavi_conv_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                  c_int, c_void_p]),
-    "selavi_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_ll]),
+    "selavi_wgrad_workspace_bytes": (c_size_t, [c_void_p]),
     "selavi_conv_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                   c_int, c_int, c_void_p]),
     "selavi_bn_reduce_partials": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -302,34 +302,74 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// bf16x3 variant: both operands stay MN-major (channels contiguous, exactly as they lie in HBM) — supported by
-// tcgen05.mma.kind::f16 (probed: profiles/r01_umma_probe_bf16.txt), so the loaders neither transpose nor gather
-// more than 32 contiguous bytes per thread; x = hi + lo with hi = bf16(x), lo = bf16(x - hi) and three MMAs
-// (lo*hi + hi*lo + hi*hi, fp32 accumulate) give ~2^-17 relative operand error, twice the tf32 MMA rate and half
-// the shared-memory bytes.  Tile layout: SWIZZLE_128B MN-major atoms [k-group of 8 pixels][chunk of 64 channels].
-__device__ __forceinline__ void split_bf16x8(const float4& p, const float4& q, uint4& hi, uint4& lo) {
-    const float x[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat162 hb = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
-        const __nv_bfloat162 lb = __floats2bfloat162_rn(x[2 * i] - __low2float(hb), x[2 * i + 1] - __high2float(hb));
-        h[i] = *reinterpret_cast<const uint32_t*>(&hb);
-        l[i] = *reinterpret_cast<const uint32_t*>(&lb);
+// bf16x3 variant (default).  Both operands stay MN-major (channels contiguous, exactly as they lie in HBM) —
+// supported by tcgen05.mma.kind::f16 (probed: profiles/r01_umma_probe_bf16.txt) but not by kind::tf32.
+//   1. split_bf16_kernel (one pass per operand): x = hi + lo, hi = bf16(x), lo = bf16(x - hi); for the conv input it
+//      also applies the pending BN+ReLU of the previous layer.  ~2^-17 relative operand error with three MMAs
+//      (lo*hi + hi*lo + hi*hi, fp32 accumulate), twice the tf32 MMA rate and half the shared-memory bytes.
+//   2. wgrad_bf16_kernel: the loaders are pure 16-byte cp.async copies (8 channels of one pixel, zero-filled outside the
+//      image) straight into SWIZZLE_128B MN-major atoms [k-group of 8 pixels][chunk of 64 channels]; no register
+//      staging, no conversion, ~6x fewer instructions per stage than the register-staged tf32 loader (ncu:
+//      profiles/r01b_wgrad_notes.txt).
+__global__ void split_bf16_kernel(const float4* __restrict__ src, const float4* __restrict__ scale,
+                                  const float4* __restrict__ shift, int relu, uint2* __restrict__ hi, uint2* __restrict__ lo,
+                                  long long total4, int c4n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        float4 x = src[i];
+        if (scale) {
+            const int c4 = (int)(i % c4n);
+            const float4 sc = __ldg(scale + c4), sf = __ldg(shift + c4);
+            x.x = fmaf(x.x, sc.x, sf.x);
+            x.y = fmaf(x.y, sc.y, sf.y);
+            x.z = fmaf(x.z, sc.z, sf.z);
+            x.w = fmaf(x.w, sc.w, sf.w);
+            if (relu) {
+                x.x = fmaxf(x.x, 0.f);
+                x.y = fmaxf(x.y, 0.f);
+                x.z = fmaxf(x.z, 0.f);
+                x.w = fmaxf(x.w, 0.f);
+            }
+        }
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(x.x - __low2float(h0), x.y - __high2float(h0));
+        const __nv_bfloat162 l1 = __floats2bfloat162_rn(x.z - __low2float(h1), x.w - __high2float(h1));
+        hi[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        lo[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
     }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-constexpr int WB_LOADER_WARPS = 8;              // 4 per scheduler: the gather/convert streams are latency-bound
-constexpr int WB_A_PER = 512 / (WB_LOADER_WARPS * 32);   // A units (pixel, 8 channels) per thread and stage
-constexpr int WB_B_PER = 1024 / (WB_LOADER_WARPS * 32);  // B units per thread and stage
+struct WgradBf16Params {
+    const __nv_bfloat16* a_hi;  // conv input activation, normalised + split  [pixels_in][cs]
+    const __nv_bfloat16* a_lo;
+    const __nv_bfloat16* z_hi;  // gradient wrt the conv output, split         [M][cd]
+    const __nv_bfloat16* z_lo;
+    float* partial;
+    int nb, ts, hs, ws, cs;
+    int td, hd, wd, cd;
+    int kt, kh, kw, st, sh, sw, pt, ph, pw;
+    int M;
+    int mtiles, bnt, ntiles;
+    int stages, total_kstages, kstages_per_slice;
+    int passes;
+    uint32_t tmem_cols;
+};
+
+constexpr int WB_LOADER_WARPS = 8;
 constexpr int WB_MMA_WARP = WB_LOADER_WARPS;
 constexpr int WB_THREADS = (WB_LOADER_WARPS + 1) * 32;
 constexpr int WB_LTHREADS = WB_LOADER_WARPS * 32;
-constexpr int WB_A_BYTES = 4 * 2 * 1024;   // 4 k-groups x 2 chunks of 64 channels
+constexpr int WB_A_BYTES = 4 * 2 * 1024;   // 4 k-groups x 2 chunks of 64 channels (bf16)
 
-__global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradParams p) {
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+__global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf16Params p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int nchb = (p.bnt + 63) >> 6;              // 64-channel chunks of the B tile
@@ -369,36 +409,23 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradPa
     const int n_off = ntile * p.bnt;
 
     if (warp < WB_LOADER_WARPS) {
-        const int C4 = p.cs >> 2;
+        const int C8 = p.cs >> 3;
         const int taps = p.kt * p.kh * p.kw;
-        const bool pro = p.pro_scale != nullptr;
-        // ---- A units (pixel, 8-row group): u = tid + 256*j, px = u >> 4, g8 = u & 15; the two 4-channel halves of a
-        //      unit are independent flattened K chunks (tap, c4) — fixed per thread for the whole kernel
+        // ---- A units (pixel, 8 GEMM rows): u = tid + 256*j, px = (tid >> 4) + 16*j, g8 = tid & 15; the 8 rows are the
+        //      flattened K chunk (tap, c8) — fixed per thread for the whole kernel (cs is a multiple of 8)
         const int g8a = tid & 15;
-        int a_kt[2], a_kh[2], a_kw[2], a_c4[2];
-        bool a_valid[2];
-        float4 a_sc[2], a_sf[2];
+        const int Q8 = mt * 16 + g8a;
+        const int tap = Q8 / C8;
+        const int a_coff = (Q8 % C8) * 8;
+        const bool a_valid = tap < taps;
+        const int a_kw = tap % p.kw, a_kh = (tap / p.kw) % p.kh, a_kt = tap / (p.kw * p.kh);
+        uint32_t a_soff[2];
+        int cw[2], ch_[2], ct[2], cn[2];
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            const int Q = (mt * 16 + g8a) * 2 + hf;
-            const int tap = Q / C4;
-            a_c4[hf] = Q % C4;
-            a_valid[hf] = tap < taps;
-            a_kw[hf] = tap % p.kw;
-            a_kh[hf] = (tap / p.kw) % p.kh;
-            a_kt[hf] = tap / (p.kw * p.kh);
-            a_sc[hf] = make_float4(1.f, 1.f, 1.f, 1.f);
-            a_sf[hf] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pro && a_valid[hf]) {
-                a_sc[hf] = __ldg(reinterpret_cast<const float4*>(p.pro_scale + a_c4[hf] * 4));
-                a_sf[hf] = __ldg(reinterpret_cast<const float4*>(p.pro_shift + a_c4[hf] * 4));
-            }
-        }
-        // coordinates of this thread's two A pixels (px = tid>>4 and 16 + tid>>4), advanced by 32 pixels per stage
-        int cw[WB_A_PER], ch_[WB_A_PER], ct[WB_A_PER], cn[WB_A_PER];
-#pragma unroll
-        for (int j = 0; j < WB_A_PER; ++j) {
-            const int m = ks_begin * WG_PIX + (tid >> 4) + (WB_LTHREADS >> 4) * j;
+        for (int j = 0; j < 2; ++j) {
+            const int px = (tid >> 4) + 16 * j;
+            a_soff[j] = (uint32_t)(((px >> 3) * 2 + (g8a >> 3)) * 1024 + (px & 7) * 128 + (((g8a & 7) ^ (px & 7)) << 4));
+            const int m = ks_begin * WG_PIX + px;
             cw[j] = m % p.wd;
             const int t1 = m / p.wd;
             ch_[j] = t1 % p.hd;
@@ -406,53 +433,44 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradPa
             ct[j] = t2 % p.td;
             cn[j] = t2 / p.td;
         }
-        // ---- B units (pixel, 8-channel group): u = tid + 256*j, px = u / upp, g8 = u % upp
+        // ---- B units (pixel, 8 channels of dz): u = tid + 256*j, px = u / upp, g8 = u % upp
         const int upp = (p.bnt + 7) >> 3;
-        int b_px[WB_B_PER], b_g8[WB_B_PER];
+        int b_px[4];
+        uint32_t b_soff[4];
+        long long b_goff[4];   // element offset of the unit inside a stage: px*cd + n_off + g8*8 (or -1)
 #pragma unroll
-        for (int j = 0; j < WB_B_PER; ++j) {
+        for (int j = 0; j < 4; ++j) {
             const int u = tid + WB_LTHREADS * j;
-            b_px[j] = u / upp;
-            b_g8[j] = u % upp;
-            if (b_px[j] >= WG_PIX) b_px[j] = -1;
+            const int px = u / upp, g8 = u % upp;
+            const int c0 = n_off + g8 * 8;
+            const bool ok = px < WG_PIX && c0 < p.cd;
+            b_px[j] = ok ? px : -1;
+            b_soff[j] = (uint32_t)(((px >> 3) * nchb + (g8 >> 3)) * 1024 + (px & 7) * 128 + (((g8 & 7) ^ (px & 7)) << 4));
+            b_goff[j] = (long long)px * p.cd + c0;
         }
-        int ks_g = ks_begin;
-        struct BStage {
-            float4 a[WB_A_PER][2];   // [pixel j][half]
-            float4 b[WB_B_PER][2];   // [unit j][half]
-        };
-        auto gather = [&](BStage& s) {
+        int stage = 0;
+        uint32_t phase = 0;
+        int prev_stage = -1;
+        const bool with_lo = p.passes == 3;
+        for (int i = 0; i < nks; ++i) {
+            const int ks = ks_begin + i;
+            sv::mbar_wait(&empty_bar[stage], phase ^ 1);
+            const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t a_lo = a_hi + WB_A_BYTES;
+            const uint32_t b_hi = a_lo + WB_A_BYTES;
+            const uint32_t b_lo = b_hi + b_bytes;
 #pragma unroll
-            for (int j = 0; j < WB_A_PER; ++j) {
-                const int m = ks_g * WG_PIX + (tid >> 4) + (WB_LTHREADS >> 4) * j;
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (m < p.M && a_valid[hf]) {
-                        const int a = ct[j] * p.st - p.pt + a_kt[hf];
-                        const int b = ch_[j] * p.sh - p.ph + a_kh[hf];
-                        const int d = cw[j] * p.sw - p.pw + a_kw[hf];
-                        if ((a >= 0) & (a < p.ts) & (b >= 0) & (b < p.hs) & (d >= 0) & (d < p.ws)) {
-                            const size_t pix = (size_t)((cn[j] * p.ts + a) * p.hs + b) * p.ws + d;
-                            x = __ldg(reinterpret_cast<const float4*>(p.src + pix * p.cs + a_c4[hf] * 4));
-                            if (pro) {
-                                x.x = fmaf(x.x, a_sc[hf].x, a_sf[hf].x);
-                                x.y = fmaf(x.y, a_sc[hf].y, a_sf[hf].y);
-                                x.z = fmaf(x.z, a_sc[hf].z, a_sf[hf].z);
-                                x.w = fmaf(x.w, a_sc[hf].w, a_sf[hf].w);
-                                if (p.pro_relu) {
-                                    x.x = fmaxf(x.x, 0.f);
-                                    x.y = fmaxf(x.y, 0.f);
-                                    x.z = fmaxf(x.z, 0.f);
-                                    x.w = fmaxf(x.w, 0.f);
-                                }
-                            }
-                        }
-                    }
-                    s.a[j][hf] = x;
-                }
-                // advance this pixel by WG_PIX for the next stage
-                cw[j] += WG_PIX;
+            for (int j = 0; j < 2; ++j) {
+                const int m = ks * WG_PIX + (tid >> 4) + 16 * j;
+                const int a = ct[j] * p.st - p.pt + a_kt;
+                const int b = ch_[j] * p.sh - p.ph + a_kh;
+                const int d = cw[j] * p.sw - p.pw + a_kw;
+                const bool ok = a_valid & (m < p.M) & (a >= 0) & (a < p.ts) & (b >= 0) & (b < p.hs) & (d >= 0) & (d < p.ws);
+                const size_t off = ok ? ((size_t)(((cn[j] * p.ts + a) * p.hs + b) * p.ws + d) * p.cs + a_coff) : 0;
+                const uint32_t nbytes = ok ? 16u : 0u;
+                cp_async16(a_hi + a_soff[j], p.a_hi + off, nbytes);
+                if (with_lo) cp_async16(a_lo + a_soff[j], p.a_lo + off, nbytes);
+                cw[j] += WG_PIX;  // advance this pixel by one stage
                 while (cw[j] >= p.wd) {
                     cw[j] -= p.wd;
                     if (++ch_[j] == p.hd) {
@@ -464,76 +482,42 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradPa
                     }
                 }
             }
+            const long long zbase = (long long)ks * WG_PIX * p.cd;
 #pragma unroll
-            for (int j = 0; j < WB_B_PER; ++j) {
-                s.b[j][0] = s.b[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 4; ++j) {
                 if (b_px[j] >= 0) {
-                    const int m = ks_g * WG_PIX + b_px[j];
-                    const int c0 = n_off + b_g8[j] * 8;
-                    if (m < p.M) {
-                        const float* zp = p.dz + (size_t)m * p.cd + c0;
-                        if (c0 < p.cd) s.b[j][0] = __ldg(reinterpret_cast<const float4*>(zp));
-                        if (c0 + 4 < p.cd) s.b[j][1] = __ldg(reinterpret_cast<const float4*>(zp + 4));
-                    }
+                    const bool ok = ks * WG_PIX + b_px[j] < p.M;
+                    const size_t off = ok ? (size_t)(zbase + b_goff[j]) : 0;
+                    const uint32_t nbytes = ok ? 16u : 0u;
+                    cp_async16(b_hi + b_soff[j], p.z_hi + off, nbytes);
+                    if (with_lo) cp_async16(b_lo + b_soff[j], p.z_lo + off, nbytes);
                 }
             }
-            ++ks_g;
-        };
-        int stage = 0;
-        uint32_t phase = 0;
-        auto commit = [&](const BStage& s) {
-            sv::mbar_wait(&empty_bar[stage], phase ^ 1);
-            const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint32_t a_lo = a_hi + WB_A_BYTES;
-            const uint32_t b_hi = a_lo + WB_A_BYTES;
-            const uint32_t b_lo = b_hi + b_bytes;
-            const bool with_lo = p.passes == 3;
-#pragma unroll
-            for (int j = 0; j < WB_A_PER; ++j) {
-                const int px = (tid >> 4) + (WB_LTHREADS >> 4) * j;
-                uint4 hi, lo;
-                split_bf16x8(s.a[j][0], s.a[j][1], hi, lo);
-                const uint32_t off = (uint32_t)(((px >> 3) * 2 + (g8a >> 3)) * 1024 + (px & 7) * 128 + (((g8a & 7) ^ (px & 7)) << 4));
-                wg_st4(a_hi + off, hi.x, hi.y, hi.z, hi.w);
-                if (with_lo) wg_st4(a_lo + off, lo.x, lo.y, lo.z, lo.w);
+            cp_async_commit();
+            if (prev_stage >= 0) {   // the previous stage's copies have landed: publish it to the MMA warp
+                cp_async_wait<1>();
+                sv::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) sv::mbar_arrive(&full_bar[prev_stage]);
             }
-#pragma unroll
-            for (int j = 0; j < WB_B_PER; ++j) {
-                if (b_px[j] >= 0) {
-                    const int px = b_px[j], g8 = b_g8[j];
-                    uint4 hi, lo;
-                    split_bf16x8(s.b[j][0], s.b[j][1], hi, lo);
-                    const uint32_t off = (uint32_t)(((px >> 3) * nchb + (g8 >> 3)) * 1024 + (px & 7) * 128 + (((g8 & 7) ^ (px & 7)) << 4));
-                    wg_st4(b_hi + off, hi.x, hi.y, hi.z, hi.w);
-                    if (with_lo) wg_st4(b_lo + off, lo.x, lo.y, lo.z, lo.w);
-                }
-            }
-            sv::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) sv::mbar_arrive(&full_bar[stage]);
+            prev_stage = stage;
             if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1;
             }
-        };
-        BStage sa, sb;
-        gather(sa);
-        for (int i = 0; i < nks; i += 2) {
-            if (i + 1 < nks) gather(sb);
-            commit(sa);
-            if (i + 1 < nks) {
-                if (i + 2 < nks) gather(sa);
-                commit(sb);
-            }
         }
+        cp_async_wait<0>();
+        sv::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && prev_stage >= 0) sv::mbar_arrive(&full_bar[prev_stage]);
+
         // ---- epilogue: TMEM -> partial[slice][mt*128 + row][ntile*bnt + col]
         sv::mbar_wait(accum_bar, 0);
         sv::tc_fence_after();
-        const int quad = warp & 3, part = warp >> 2;            // WB_LOADER_WARPS / 4 column parts
+        const int quad = warp & 3, half = warp >> 2;
         const int units = p.bnt >> 4;
-        constexpr int PARTS = WB_LOADER_WARPS / 4;
-        const int u_begin = (units * part) / PARTS;
-        const int u_end = (units * (part + 1)) / PARTS;
+        const int u_begin = half == 0 ? 0 : (units + 1) / 2;
+        const int u_end = half == 0 ? (units + 1) / 2 : units;
         const int row = quad * 32 + lane;
         const int ntot = p.ntiles * p.bnt;
         float* out_row = p.partial + ((size_t)slice * (p.mtiles * 128) + mt * 128 + row) * ntot + n_off;
@@ -641,16 +625,27 @@ WgPlan wg_plan(int co, int taps, int cs, long long M) {
 
 }  // namespace
 
-extern "C" size_t selavi_wgrad_workspace_bytes(int co, int taps, int cs, long long M) {
-    const WgPlan pl = wg_plan(co, taps, cs, M);
-    return (size_t)pl.slices * pl.mtiles * 128 * pl.ntiles * pl.bnt * sizeof(float);
+namespace {
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+}
+
+// workspace: [split-K partial tiles][a_hi][a_lo][z_hi][z_lo] (the bf16 operand copies are only used by the bf16 path)
+extern "C" size_t selavi_wgrad_workspace_bytes(const int* geom) {
+    if (!geom) return 0;
+    const long long M = (long long)geom[1] * geom[6] * geom[7] * geom[8];
+    const long long Min = (long long)geom[1] * geom[2] * geom[3] * geom[4];
+    const int taps = geom[10] * geom[11] * geom[12];
+    const WgPlan pl = wg_plan(geom[19], taps, geom[5], M);
+    const size_t partial = (size_t)pl.slices * pl.mtiles * 128 * pl.ntiles * pl.bnt * sizeof(float);
+    return align256(partial) + 2 * align256((size_t)Min * geom[5] * 2) + 2 * align256((size_t)M * geom[9] * 2) + 256;
 }
 
 // geom: same 20 ints as selavi_conv_gemm with mode 0 (the FORWARD geometry of the convolution); dz is [M, cd].
 extern "C" int selavi_conv_wgrad(const float* src, const float* dz, float* dW, const int* geom, int ci_real,
                                  const float* pro_scale, const float* pro_shift, int pro_relu, void* workspace,
-                                 int accumulate, int passes, void* stream) {
+                                 int accumulate, int passes, void* stream_) {
     if (!src || !dz || !dW || !geom || !workspace) return selavi_fail(-1, "conv_wgrad: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
     WgradParams p;
     p.src = src;
     p.dz = dz;
@@ -663,12 +658,13 @@ extern "C" int selavi_conv_wgrad(const float* src, const float* dz, float* dW, c
     p.st = geom[13]; p.sh = geom[14]; p.sw = geom[15];
     p.pt = geom[16]; p.ph = geom[17]; p.pw = geom[18];
     const int co = geom[19];
-    if ((p.cs & 3) || (p.cd & 3)) return selavi_fail(-1, "conv_wgrad: channel strides must be multiples of 4");
+    if ((p.cs & 7) || (p.cd & 7)) return selavi_fail(-1, "conv_wgrad: channel strides must be multiples of 8");
     // passes: 3 = bf16x3 / 1 = bf16 (MN-major kind::f16 kernel); 13 = tf32x3 / 11 = tf32 (K-major transposing kernel)
     if (passes != 1 && passes != 3 && passes != 11 && passes != 13) return selavi_fail(-1, "conv_wgrad: passes must be 1, 3, 11 or 13");
     if ((pro_scale == nullptr) != (pro_shift == nullptr)) return selavi_fail(-1, "conv_wgrad: prologue needs scale and shift");
     const long long M = (long long)p.nb * p.td * p.hd * p.wd;
-    if (M <= 0 || M > 0x7fffffffLL) return selavi_fail(-1, "conv_wgrad: bad pixel count");
+    const long long Min = (long long)p.nb * p.ts * p.hs * p.ws;
+    if (M <= 0 || M > 0x7fffffffLL || Min > 0x7fffffffLL) return selavi_fail(-1, "conv_wgrad: bad pixel count");
     p.M = (int)M;
     const int taps = p.kt * p.kh * p.kw;
     const WgPlan pl = wg_plan(co, taps, p.cs, M);
@@ -689,19 +685,42 @@ extern "C" int selavi_conv_wgrad(const float* src, const float* dz, float* dW, c
     const size_t smem = (size_t)stages * stage_bytes + tail_bytes + 1024;
     dim3 grid(pl.mtiles * pl.ntiles, pl.slices);
     if (bf16) {
+        // operand preparation: normalise + split the conv input, split dz (one HBM pass each)
+        const size_t partial_bytes = align256((size_t)pl.slices * pl.mtiles * 128 * pl.ntiles * pl.bnt * sizeof(float));
+        unsigned char* w = reinterpret_cast<unsigned char*>(workspace) + partial_bytes;
+        const size_t a_bytes = align256((size_t)Min * p.cs * 2), z_bytes = align256((size_t)M * p.cd * 2);
+        WgradBf16Params q;
+        q.a_hi = reinterpret_cast<const __nv_bfloat16*>(w);
+        q.a_lo = reinterpret_cast<const __nv_bfloat16*>(w + a_bytes);
+        q.z_hi = reinterpret_cast<const __nv_bfloat16*>(w + 2 * a_bytes);
+        q.z_lo = reinterpret_cast<const __nv_bfloat16*>(w + 2 * a_bytes + z_bytes);
+        const long long a4 = Min * (p.cs / 4), z4 = M * (p.cd / 4);
+        auto blocks = [](long long n) { long long b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); };
+        split_bf16_kernel<<<blocks(a4), 256, 0, stream>>>((const float4*)src, (const float4*)pro_scale, (const float4*)pro_shift,
+                                                          pro_relu, (uint2*)q.a_hi, (uint2*)q.a_lo, a4, p.cs / 4);
+        split_bf16_kernel<<<blocks(z4), 256, 0, stream>>>((const float4*)dz, nullptr, nullptr, 0, (uint2*)q.z_hi, (uint2*)q.z_lo,
+                                                          z4, p.cd / 4);
+        SV_CUDA_CHECK(cudaGetLastError(), "conv_wgrad: split launch");
+        q.partial = p.partial;
+        q.nb = p.nb; q.ts = p.ts; q.hs = p.hs; q.ws = p.ws; q.cs = p.cs;
+        q.td = p.td; q.hd = p.hd; q.wd = p.wd; q.cd = p.cd;
+        q.kt = p.kt; q.kh = p.kh; q.kw = p.kw; q.st = p.st; q.sh = p.sh; q.sw = p.sw; q.pt = p.pt; q.ph = p.ph; q.pw = p.pw;
+        q.M = p.M; q.mtiles = p.mtiles; q.bnt = p.bnt; q.ntiles = p.ntiles;
+        q.stages = p.stages; q.total_kstages = p.total_kstages; q.kstages_per_slice = p.kstages_per_slice;
+        q.passes = p.passes; q.tmem_cols = p.tmem_cols;
         SV_CUDA_CHECK(cudaFuncSetAttribute(wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                       "conv_wgrad: cudaFuncSetAttribute");
-        wgrad_bf16_kernel<<<grid, WB_THREADS, smem, (cudaStream_t)stream>>>(p);
+        wgrad_bf16_kernel<<<grid, WB_THREADS, smem, stream>>>(q);
     } else {
         SV_CUDA_CHECK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                       "conv_wgrad: cudaFuncSetAttribute");
-        wgrad_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(p);
+        wgrad_kernel<<<grid, WG_THREADS, smem, stream>>>(p);
     }
     SV_CUDA_CHECK(cudaGetLastError(), "conv_wgrad: launch");
     const size_t total = (size_t)co * ci_real * taps;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    wgrad_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p.partial, pl.slices, pl.mtiles * 128, pl.ntiles * pl.bnt,
+    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, pl.slices, pl.mtiles * 128, pl.ntiles * pl.bnt,
                                                                   co, ci_real, taps, p.cs, dW, accumulate);
     SV_CUDA_CHECK(cudaGetLastError(), "conv_wgrad: reduce launch");
     return 0;

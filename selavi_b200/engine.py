@@ -2,7 +2,7 @@
 the C-ABI kernels and wires them into torch.autograd (so DDP's gradient hooks, torch optimizers and the
 reference training loop main.py:263-302 work unchanged).
 
-Data layout in HBM: activations channels-last fp32 [N,T,H,W,Cs] (Cs = channels padded to 4).  Every convolution
+Data layout in HBM: activations channels-last fp32 [N,T,H,W,Cs] (Cs = channels padded to 8).  Every convolution
 stores only its RAW output z; the following train-mode BatchNorm(+ReLU) lives as a per-channel (scale, shift)
 pair that the NEXT convolution applies on the fly in its operand loader ("pending" activation), so normalised
 activations are written to HBM only at residual joins (block outputs), after the stem and after the max-pool.
@@ -164,7 +164,7 @@ class TowerRunner:
         else:
             nb, c, h, w = x.shape
             t = 1
-        cs = ops.pad4(c)
+        cs = ops.padc(c)
         x_cl = torch.empty((nb, t, h, w, cs), dtype=torch.float32, device=x.device)
         _lib.check(lib.selavi_nchw_to_cl(_lib.ptr(x), _lib.ptr(x_cl), nb, c, t * h * w, cs, _stream()), "selavi_nchw_to_cl")
         act = Act(x_cl, c)

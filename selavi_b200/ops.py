@@ -2,7 +2,7 @@
 
 Tensors are torch CUDA tensors used purely as device memory; every function launches on the current stream
 and returns without synchronising.  Activations are channels-last fp32 `[N, T, H, W, Cs]` with `Cs` = channel
-count padded to a multiple of 4 (pad channels are zero).  No CPU fallback: a missing library raises.
+count padded to a multiple of 8 (pad channels are zero).  No CPU fallback: a missing library raises.
 """
 import ctypes
 
@@ -33,16 +33,20 @@ class _Prof:
             PROFILE.append((self.kind, self.flops, self.e0, self.e1))
 
 
-def pad4(c):
-    return (c + 3) & ~3
+def padc(c):
+    """channel stride of an activation with c channels: padded to 8 (32-byte rows of 8 fp32 / 16-byte units of 8 bf16)"""
+    return (c + 7) & ~7
+
+
+pad4 = padc  # historical name
 
 
 def to_channels_last(x):
-    """[N,C,T,H,W] or [N,C,H,W] (any float dtype) -> contiguous fp32 [N,T,H,W,pad4(C)]."""
+    """[N,C,T,H,W] or [N,C,H,W] (any float dtype) -> contiguous fp32 [N,T,H,W,padc(C)]."""
     if x.dim() == 4:
         x = x.unsqueeze(2)
     n, c, t, h, w = x.shape
-    out = torch.zeros((n, t, h, w, pad4(c)), dtype=torch.float32, device=x.device)
+    out = torch.zeros((n, t, h, w, padc(c)), dtype=torch.float32, device=x.device)
     out[..., :c] = x.permute(0, 2, 3, 4, 1)
     return out
 
@@ -64,7 +68,7 @@ class ConvGeom:
         self.to = (self.ti + 2 * self.pt - self.kt) // self.st + 1
         self.ho = (self.hi + 2 * self.ph - self.kh) // self.sh + 1
         self.wo = (self.wi + 2 * self.pw - self.kw) // self.sw + 1
-        self.cis, self.cos = pad4(ci), pad4(co)
+        self.cis, self.cos = padc(ci), padc(co)
         self.taps = self.kt * self.kh * self.kw
         self.m_out = nb * self.to * self.ho * self.wo
         self.m_in = nb * self.ti * self.hi * self.wi
@@ -154,7 +158,7 @@ def conv_wgrad(x, dz, geom, dw, scale=None, shift=None, relu=False, accumulate=F
     if not (dw.is_cuda and dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == geom.co * geom.ci * geom.taps):
         raise ValueError("dw must be a contiguous fp32 CUDA tensor in the torch weight layout")
     lib = _lib.lib()
-    nbytes = lib.selavi_wgrad_workspace_bytes(geom.co, geom.taps, geom.cis, geom.m_out)
+    nbytes = lib.selavi_wgrad_workspace_bytes(geom.arr(0))
     key = (x.device.index, torch.cuda.current_stream().cuda_stream)
     ws = _wgrad_ws.get(key)
     if ws is None or ws.numel() < nbytes:
