@@ -59,7 +59,8 @@ struct ConvParams {
     uint32_t tmem_cols;          // 2 accumulators of bnt columns, power of two
 };
 
-__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+// hi = x rounded to tf32 (round half up on the magnitude), so that lo = x - hi is exact, |lo| <= 2^-12 |x| and unbiased
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -458,7 +459,7 @@ __global__ void conv_pack_weights_kernel(const float* __restrict__ W, int mode, 
                 if (nn < ci && kc < co) val = W[((size_t)kc * ci + nn) * taps + tap];
             }
         }
-        const float hi = __uint_as_float(__float_as_uint(val) & 0xFFFFE000u);
+        const float hi = __uint_as_float((__float_as_uint(val) + 0x1000u) & 0xFFFFE000u);
         const float lo = val - hi;
         float* base = out + blk * (size_t)(2 * bnt * 32);
         const int pos = n * 32 + ((c ^ (n & 7)) << 2) + e;

@@ -61,7 +61,10 @@ def test_train_step_matches_reference(cuda_device, name):
             n = key[len("grad64/"):]
             e = _rel(grads[n].detach().cpu().numpy(), gold[key])
             worst_t = max(worst_t, e)
-            assert e < 5 * gtol, (n, e, _rel(gold["grad/" + n], gold[key]))
+            # some gradients (first conv after 37 BN layers) are ill-conditioned: the reference's own fp32 result is
+            # 6e-3 off its fp64 result there; allow 8x the reference's own error (tf32x3 carries ~2^-21 per operand)
+            ref_err = _rel(gold["grad/" + n], gold[key])
+            assert e < max(5 * gtol, 8 * ref_err), (n, e, ref_err)
     print(f"{name}: worst grad-norm err {worst:.2e}, worst grad-tensor err {worst_t:.2e}")
     sd = m.state_dict()
     for key in gold.files:
