@@ -82,6 +82,18 @@ size_t selavi_wgrad_workspace_bytes(const int* geom);
 int selavi_conv_wgrad(const float* src, const float* dz, float* dW, const int* geom, int ci_real,
                       const float* pro_scale, const float* pro_shift, int pro_relu, void* workspace, int accumulate,
                       int passes, void* stream);
+/* bf16x3 backward on pre-split gradients: z_hi/z_lo = bf16 hi/lo planes [M, cd] of the gradient wrt the conv output
+ * (from selavi_bn_bwd_apply or selavi_split_bf16).  wgrad_bf16: same contract as selavi_conv_wgrad (passes 3 or 1).
+ * dgrad_bf16: geom in mode 1; wpack from selavi_dgrad_pack_weights (W[co][ci][taps], cs = channel stride of dz). */
+int selavi_split_bf16(const float* x, const float* scale, const float* shift, int relu, void* hi, void* lo, long long M,
+                      int cs, void* stream);
+int selavi_conv_wgrad_bf16(const float* src, const void* z_hi, const void* z_lo, float* dW, const int* geom, int ci_real,
+                           const float* pro_scale, const float* pro_shift, int pro_relu, void* workspace, int accumulate,
+                           int passes, void* stream);
+size_t selavi_dgrad_wpack_bytes(int ci, int k_total);
+int selavi_dgrad_pack_weights(const float* W, int co, int ci, int taps, int cs, void* wpack, void* stream);
+int selavi_conv_dgrad_bf16(const void* z_hi, const void* z_lo, float* dx, const void* wpack, const int* geom,
+                           int accumulate, int passes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm (train mode, nn.BatchNorm{1,2,3}d / SyncBatchNorm semantics), residual add, ReLU, pooling, layout,
@@ -92,7 +104,8 @@ int selavi_conv_wgrad(const float* src, const float* dz, float* dW, const int* g
  *   apply:           out = act(z*scale+shift [+ res | + res*rscale+rshift])  (tv:video/resnet.py:107-119)
  *   bwd_reduce:      sums [2][cs] = (sum g, sum g*zhat), g masked by the following ReLU:
  *                    mask_mode 0 none, 1 act>0 (materialised block output), 2 z*scale+shift>0
- *   bwd_apply:       dz = scale*(g - sum_g/count - zhat*sum_gz/count); optional gres (+)= masked g
+ *   bwd_apply:       dz = scale*(g - sum_g/count - zhat*sum_gz/count) as fp32 (dz, nullable) and/or as bf16 hi/lo
+ *                    planes (dz_hi/dz_lo, nullable) for the bf16x3 gradient kernels; optional gres (+)= masked g
  */
 int selavi_bn_reduce_partials(const float* partial, int tiles, int ctot, int cs, double* sums, void* stream);
 int selavi_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
@@ -108,7 +121,8 @@ int selavi_bn_bwd_reduce(const float* g, const float* z, const float* act, int m
                          double* sums, void* stream);
 int selavi_bn_bwd_apply(const float* g, const float* z, const float* act, int mask_mode, const float* scale,
                         const float* shift, const float* mean, const float* invstd, const double* sums, double count,
-                        long long M, int cs, float* dz, float* gres, int gres_accumulate, void* stream);
+                        long long M, int cs, float* dz, float* gres, int gres_accumulate, void* dz_hi, void* dz_lo,
+                        void* stream);
 int selavi_relu_bwd(const float* g, const float* act, float* out, long long n, int accumulate, void* stream);
 /* MaxPool2d(3,2,1) over relu(z*scale+shift) (tv:resnet.py:268-271) and its gradient wrt that activation */
 int selavi_maxpool3x3s2_fwd(const float* z, const float* scale, const float* shift, float* out, int nb, int h, int w,

@@ -47,7 +47,13 @@ SIGNATURES = {
     "selavi_bn_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_ll,
                                      c_int, c_void_p, c_void_p, c_void_p]),
     "selavi_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                    c_double, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+                                    c_double, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "selavi_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "selavi_conv_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                       c_void_p, c_int, c_int, c_void_p]),
+    "selavi_dgrad_wpack_bytes": (c_size_t, [c_int, c_int]),
+    "selavi_dgrad_pack_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "selavi_conv_dgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "selavi_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "selavi_maxpool3x3s2_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "selavi_maxpool3x3s2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
@@ -91,14 +97,15 @@ class SelaviError(RuntimeError):
 
 # kernels launched per C-ABI call (for bench.py's `gpu_launches` claim); host-only queries launch none
 KERNELS_PER_CALL = {
-    "selavi_sk_solve": 1, "selavi_sk_softmax_product": 1, "selavi_conv_pack_weights": 1, "selavi_conv_gemm": 1, "selavi_conv_wgrad": 2,
+    "selavi_sk_solve": 1, "selavi_sk_softmax_product": 1, "selavi_conv_pack_weights": 1, "selavi_conv_gemm": 1, "selavi_conv_wgrad": 4,
     "selavi_bn_reduce_partials": 1, "selavi_bn_finalize": 1, "selavi_bn_eval_affine": 1, "selavi_bn_apply": 1,
     "selavi_bn_bwd_reduce": 2, "selavi_bn_bwd_apply": 1, "selavi_relu_bwd": 1, "selavi_maxpool3x3s2_fwd": 1,
     "selavi_maxpool3x3s2_bwd": 1, "selavi_avgpool_fwd": 1, "selavi_avgpool_bwd": 1, "selavi_nchw_to_cl": 1,
     "selavi_sgd_step": 1, "selavi_bgemm": 1, "selavi_heads_bn_stats": 1, "selavi_heads_bn_finalize": 1,
     "selavi_heads_bn_eval_affine": 1, "selavi_heads_act": 1, "selavi_heads_bn_bwd_reduce": 1,
     "selavi_heads_bn_bwd_apply": 1, "selavi_heads_sum_masked": 1, "selavi_heads_colsum": 1, "selavi_ce_loss": 2,
-    "selavi_debug_umma_probe": 1, "selavi_mel_logfbank": 1,
+    "selavi_debug_umma_probe": 1, "selavi_mel_logfbank": 1, "selavi_split_bf16": 1, "selavi_conv_wgrad_bf16": 3,
+    "selavi_dgrad_pack_weights": 1, "selavi_conv_dgrad_bf16": 1,
 }
 COUNT_CALLS = False
 CALLS = {}

@@ -1,0 +1,408 @@
+// Data gradient of the implicit-GEMM convolution in bf16x3 on tcgen05 (kind::f16), fed by cp.async.
+//
+//   dx[m, ci] (+)= sum_{tap, co} dz[pix(m, tap), co] * W[co, ci, tap]        m = input pixel of the forward conv
+//
+// Replaces cuDNN's dgrad in loss.backward() (main.py:298) for every conv of model.py:93-121.  The gradient dz
+// arrives already split into bf16 hi/lo planes (written by the BatchNorm-backward kernel, see elem.cu), so the
+// A-operand loaders are pure 16-byte cp.async copies (8 channels of one gathered pixel, zero-filled where the
+// transposed gather falls outside the image or between strides) into 128B-swizzled K-major tiles; the weights
+// are pre-tiled / pre-split bf16 (dgrad_pack_weights_bf16_kernel) and arrive by one TMA bulk copy per stage.
+// Three MMAs per k-step (lo*hi + hi*lo + hi*hi, fp32 accumulate in TMEM): ~2^-17 operand error, measured 4e-6
+// per layer — the same level as the tf32x3 forward at these K — at twice the tf32 MMA rate and half the
+// shared-memory bytes per FLOP.  Persistent CTAs, double-buffered accumulator, dedicated epilogue warps (as conv.cu).
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/selavi_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int DG_BM = 128;
+constexpr int DG_EPI_WARPS = 4;
+constexpr int DG_LOADER_WARPS = 8;
+constexpr int DG_MMA_WARP = DG_EPI_WARPS + DG_LOADER_WARPS;
+constexpr int DG_BPROD_WARP = DG_MMA_WARP + 1;
+constexpr int DG_THREADS = (DG_BPROD_WARP + 1) * 32;
+constexpr int DG_A_BYTES = DG_BM * 128;     // 128 pixels x 64 bf16 channels
+constexpr int DG_MAX_TAPS = 64;
+constexpr int DG_MAX_STAGES = 6;
+
+struct DgradParams {
+    const __nv_bfloat16* z_hi;   // [pixels_out][cs] gradient wrt the conv output, split
+    const __nv_bfloat16* z_lo;
+    float* dst;                  // [M = pixels_in][cd]
+    const unsigned char* wpack;  // [ntiles][kstages][2][BNt][128B] bf16
+    int nb, ts, hs, ws, cs;      // gathered tensor (dz) geometry: forward OUTPUT dims
+    int td, hd, wd, cd;          // dx geometry: forward INPUT dims
+    int kt, kh, kw, st, sh, sw, pt, ph, pw;
+    int M, m_tiles, kstages, bnt, ntiles, stages, accumulate, passes;
+    uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ void dg_cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(DG_THREADS, 1) dgrad_bf16_kernel(const DgradParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_tile_bytes = p.bnt * 128;
+    const int stage_bytes = 2 * DG_A_BYTES + 2 * b_tile_bytes;   // A_hi | A_lo | B_hi | B_lo
+    unsigned char* tail = smem + (size_t)p.stages * stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* empty_bar = full_bar + DG_MAX_STAGES;
+    uint64_t* tfull_bar = empty_bar + DG_MAX_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    int* tap_dt = reinterpret_cast<int*>(tmem_slot + 2);
+    int* tap_off = tap_dt + DG_MAX_TAPS;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int taps = p.kt * p.kh * p.kw;
+    const int total_tiles = p.m_tiles * p.ntiles;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            sv::mbar_init(&full_bar[s], DG_LOADER_WARPS + 1);
+            sv::mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            sv::mbar_init(&tfull_bar[a], 1);
+            sv::mbar_init(&tempty_bar[a], DG_EPI_WARPS);
+        }
+        sv::fence_barrier_init();
+    }
+    for (int t = tid; t < taps; t += DG_THREADS) {
+        const int kw_ = t % p.kw, kh_ = (t / p.kw) % p.kh, kt_ = t / (p.kw * p.kh);
+        tap_dt[t] = kt_ | (kh_ << 8) | (kw_ << 16);
+        // transposed gather: src = (dst + pad - k) / stride == floor((dst+pad)/stride) - (k >> log2(stride)) when valid
+        const int qt = p.st == 2 ? (kt_ >> 1) : kt_, qh = p.sh == 2 ? (kh_ >> 1) : kh_, qw = p.sw == 2 ? (kw_ >> 1) : kw_;
+        tap_off[t] = -((qt * p.hs + qh) * p.ws + qw);
+    }
+    if (warp == DG_MMA_WARP) {
+        sv::tmem_alloc(tmem_slot, p.tmem_cols);
+        sv::tmem_relinquish();
+    }
+    sv::tc_fence_before();
+    __syncthreads();
+    sv::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= DG_EPI_WARPS && warp < DG_MMA_WARP) {
+        // ------------------------------------------------------------------ A loaders: cp.async gathers
+        const int ltid = tid - DG_EPI_WARPS * 32;
+        const int c = ltid & 7;    // 16-byte chunk (8 channels) within the 128B K row
+        const int r0 = ltid >> 3;  // rows r0 + 32*j
+        const int C8 = p.cs >> 3;
+        const uint32_t sw_off = (uint32_t)((c ^ (r0 & 7)) << 4);
+        const bool with_lo = p.passes == 3;
+        int stage = 0, prev_stage = -1;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m0 = (tile / p.ntiles) * DG_BM;
+            int pb[4];
+            uint32_t vm[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = m0 + r0 + 32 * j;
+                pb[j] = 0;
+                vm[j] = 0;
+                if (m < p.M) {
+                    const int w_ = m % p.wd;
+                    const int t1 = m / p.wd;
+                    const int h_ = t1 % p.hd;
+                    const int t2 = t1 / p.hd;
+                    const int t_ = t2 % p.td;
+                    const int n_ = t2 / p.td;
+                    const int at = t_ + p.pt, ah = h_ + p.ph, aw = w_ + p.pw;
+                    uint32_t mt = 0, mh = 0, mw = 0;
+                    for (int k = 0; k < p.kt; ++k) {
+                        int u = at - k;
+                        bool ok = u >= 0;
+                        if (p.st == 2) { ok &= !(u & 1); u >>= 1; }
+                        mt |= (uint32_t)(ok & (u < p.ts)) << k;
+                    }
+                    for (int k = 0; k < p.kh; ++k) {
+                        int u = ah - k;
+                        bool ok = u >= 0;
+                        if (p.sh == 2) { ok &= !(u & 1); u >>= 1; }
+                        mh |= (uint32_t)(ok & (u < p.hs)) << k;
+                    }
+                    for (int k = 0; k < p.kw; ++k) {
+                        int u = aw - k;
+                        bool ok = u >= 0;
+                        if (p.sw == 2) { ok &= !(u & 1); u >>= 1; }
+                        mw |= (uint32_t)(ok & (u < p.ws)) << k;
+                    }
+                    const int bt = p.st == 2 ? (at >> 1) : at, bh = p.sh == 2 ? (ah >> 1) : ah, bw = p.sw == 2 ? (aw >> 1) : aw;
+                    pb[j] = ((n_ * p.ts + bt) * p.hs + bh) * p.ws + bw;
+                    vm[j] = mt | (mh << 8) | (mw << 16) | 0x80000000u;
+                }
+            }
+            int tap = 0, c8 = c;  // flattened K chunk q = 8*ks + c -> (tap, c8)
+            while (c8 >= C8) {
+                c8 -= C8;
+                ++tap;
+            }
+            for (int ks = 0; ks < p.kstages; ++ks) {
+                sv::mbar_wait(&empty_bar[stage], phase ^ 1);
+                const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t a_lo = a_hi + DG_A_BYTES;
+                int pk = 0, off = 0;
+                const bool kvalid = tap < taps;
+                if (kvalid) {
+                    pk = tap_dt[tap];
+                    off = tap_off[tap];
+                }
+                const int s_t = pk & 255, s_h = 8 + ((pk >> 8) & 255), s_w = 16 + ((pk >> 16) & 255);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t m_ = vm[j];
+                    const bool ok = kvalid && ((m_ >> 31) & (m_ >> s_t) & (m_ >> s_h) & (m_ >> s_w) & 1u);
+                    const size_t goff = ok ? ((size_t)(pb[j] + off) * p.cs + c8 * 8) : 0;
+                    const uint32_t nbytes = ok ? 16u : 0u;
+                    const uint32_t row_off = (uint32_t)((r0 + 32 * j) * 128) + sw_off;
+                    dg_cp_async16(a_hi + row_off, p.z_hi + goff, nbytes);
+                    if (with_lo) dg_cp_async16(a_lo + row_off, p.z_lo + goff, nbytes);
+                }
+                asm volatile("cp.async.commit_group;\n" ::: "memory");
+                if (prev_stage >= 0) {   // the previous stage's copies have landed: publish it
+                    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+                    sv::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) sv::mbar_arrive(&full_bar[prev_stage]);
+                }
+                prev_stage = stage;
+                c8 += 8;
+                while (c8 >= C8 && tap < taps) {
+                    c8 -= C8;
+                    ++tap;
+                }
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        sv::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && prev_stage >= 0) sv::mbar_arrive(&full_bar[prev_stage]);
+    } else if (warp < DG_EPI_WARPS) {
+        // ------------------------------------------------------------------ epilogue
+        const int quad = warp;
+        const int units = p.bnt >> 4;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const int m_tile = tile / p.ntiles, ntile = tile % p.ntiles;
+            const int m = m_tile * DG_BM + quad * 32 + lane;
+            const bool row_ok = m < p.M;
+            const int n_base = ntile * p.bnt;
+            float* out_row = p.dst + (size_t)(row_ok ? m : 0) * p.cd;
+            sv::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
+            sv::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * (p.tmem_cols >> 1);
+            for (int u = 0; u < units; ++u) {
+                uint32_t av[16];
+                sv::tmem_ld16(taddr + (uint32_t)(u * 16), av);
+                sv::tmem_ld_wait();
+                const int ncol = n_base + u * 16;
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        if (ncol + i < p.cd) {
+                            float4* dp = reinterpret_cast<float4*>(out_row + ncol + i);
+                            float4 o = make_float4(__uint_as_float(av[i]), __uint_as_float(av[i + 1]), __uint_as_float(av[i + 2]),
+                                                   __uint_as_float(av[i + 3]));
+                            if (p.accumulate) {
+                                const float4 old = *dp;
+                                o.x += old.x;
+                                o.y += old.y;
+                                o.z += old.z;
+                                o.w += old.w;
+                            }
+                            *dp = o;
+                        }
+                    }
+                }
+            }
+            sv::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) sv::mbar_arrive(&tempty_bar[acc]);
+        }
+    } else if (warp == DG_MMA_WARP) {
+        if (lane == 0) {
+            const uint32_t idesc = sv::make_idesc_f16(DG_BM, p.bnt, 1, 1, 0, 0);  // bf16 x bf16, K-major
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                sv::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+                sv::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * (p.tmem_cols >> 1);
+                for (int ks = 0; ks < p.kstages; ++ks) {
+                    sv::mbar_wait(&full_bar[stage], phase);
+                    sv::tc_fence_after();
+                    const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t a_lo = a_hi + DG_A_BYTES;
+                    const uint32_t b_hi = a_lo + DG_A_BYTES;
+                    const uint32_t b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {   // 4 x (K = 16 bf16 = 32 bytes)
+                        const uint64_t da_hi = sv::make_smem_desc_sw128(a_hi + k4 * 32, 16, 1024);
+                        const uint64_t db_hi = sv::make_smem_desc_sw128(b_hi + k4 * 32, 16, 1024);
+                        if (p.passes == 3) {
+                            const uint64_t da_lo = sv::make_smem_desc_sw128(a_lo + k4 * 32, 16, 1024);
+                            const uint64_t db_lo = sv::make_smem_desc_sw128(b_lo + k4 * 32, 16, 1024);
+                            sv::umma_f16(d_tmem, da_lo, db_hi, idesc, (ks | k4) ? 1u : 0u);
+                            sv::umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+                            sv::umma_f16(d_tmem, da_hi, db_hi, idesc, 1u);
+                        } else {
+                            sv::umma_f16(d_tmem, da_hi, db_hi, idesc, (ks | k4) ? 1u : 0u);
+                        }
+                    }
+                    sv::umma_commit(&empty_bar[stage]);
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                sv::umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        if (lane == 0) {   // B producer: one TMA bulk copy per stage
+            const uint32_t bytes = (uint32_t)(p.passes == 3 ? 2 * b_tile_bytes : b_tile_bytes);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int ntile = tile % p.ntiles;
+                const unsigned char* wsrc = p.wpack + (size_t)ntile * p.kstages * 2 * b_tile_bytes;
+                for (int ks = 0; ks < p.kstages; ++ks) {
+                    sv::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    sv::mbar_arrive_expect_tx(&full_bar[stage], bytes);
+                    sv::bulk_g2s(smem + (size_t)stage * stage_bytes + 2 * DG_A_BYTES, wsrc + (size_t)ks * 2 * b_tile_bytes,
+                                 bytes, &full_bar[stage]);
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == DG_MMA_WARP) {
+        sv::tc_fence_after();
+        sv::tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// W [co][ci][taps] -> B operand of the data gradient in bf16 hi/lo: n = ci, k = tap*cs + co (cs = padded co),
+// tiles [ntile][kstage of 64 k][hi|lo][bnt rows][128 B], 128B-swizzled.
+__global__ void dgrad_pack_weights_bf16_kernel(const float* __restrict__ W, int co, int ci, int taps, int cs, int bnt,
+                                               int ntiles, int kstages, __nv_bfloat16* __restrict__ out) {
+    const size_t total = (size_t)ntiles * kstages * bnt * 64;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(idx & 7);
+        const int c = (int)((idx >> 3) & 7);
+        const int n = (int)((idx >> 6) % bnt);
+        const size_t blk = (idx >> 6) / bnt;
+        const int ks = (int)(blk % kstages);
+        const int nt = (int)(blk / kstages);
+        const int k = ks * 64 + c * 8 + e;
+        const int tap = k / cs, kc = k % cs;
+        const int nn = nt * bnt + n;
+        float val = 0.f;
+        if (tap < taps && nn < ci && kc < co) val = W[((size_t)kc * ci + nn) * taps + tap];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(val - __bfloat162float(hi));
+        __nv_bfloat16* base = out + blk * (size_t)(2 * bnt * 64);
+        const int pos = n * 64 + ((c ^ (n & 7)) << 3) + e;
+        base[pos] = hi;
+        base[bnt * 64 + pos] = lo;
+    }
+}
+
+void dg_tiles(int n_out, int* bnt, int* ntiles) {
+    int nt = (n_out + 255) / 256;
+    int per = (n_out + nt - 1) / nt;
+    per = (per + 15) & ~15;
+    *bnt = per;
+    *ntiles = nt;
+}
+
+}  // namespace
+
+extern "C" size_t selavi_dgrad_wpack_bytes(int ci, int k_total) {
+    int bnt, nt;
+    dg_tiles(ci, &bnt, &nt);
+    return (size_t)nt * ((k_total + 63) / 64) * 2 * bnt * 128;
+}
+
+extern "C" int selavi_dgrad_pack_weights(const float* W, int co, int ci, int taps, int cs, void* wpack, void* stream) {
+    if (!W || !wpack || co <= 0 || ci <= 0 || taps <= 0 || (cs & 7)) return selavi_fail(-1, "dgrad_pack_weights: bad arguments");
+    int bnt, nt;
+    dg_tiles(ci, &bnt, &nt);
+    const int kstages = (taps * cs + 63) / 64;
+    const size_t total = (size_t)nt * kstages * bnt * 64;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    dgrad_pack_weights_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, co, ci, taps, cs, bnt, nt, kstages,
+                                                                             reinterpret_cast<__nv_bfloat16*>(wpack));
+    SV_CUDA_CHECK(cudaGetLastError(), "dgrad_pack_weights: launch");
+    return 0;
+}
+
+// geom: the 20-int geometry of selavi_conv_gemm in mode 1 (gathered tensor = dz with the forward OUTPUT dims, dst = dx)
+extern "C" int selavi_conv_dgrad_bf16(const void* z_hi, const void* z_lo, float* dx, const void* wpack, const int* geom,
+                                      int accumulate, int passes, void* stream) {
+    if (!z_hi || !z_lo || !dx || !wpack || !geom) return selavi_fail(-1, "conv_dgrad_bf16: null argument");
+    if (geom[0] != 1) return selavi_fail(-1, "conv_dgrad_bf16: geometry must be in dgrad mode");
+    DgradParams p;
+    p.z_hi = reinterpret_cast<const __nv_bfloat16*>(z_hi);
+    p.z_lo = reinterpret_cast<const __nv_bfloat16*>(z_lo);
+    p.dst = dx;
+    p.wpack = reinterpret_cast<const unsigned char*>(wpack);
+    p.nb = geom[1]; p.ts = geom[2]; p.hs = geom[3]; p.ws = geom[4]; p.cs = geom[5];
+    p.td = geom[6]; p.hd = geom[7]; p.wd = geom[8]; p.cd = geom[9];
+    p.kt = geom[10]; p.kh = geom[11]; p.kw = geom[12];
+    p.st = geom[13]; p.sh = geom[14]; p.sw = geom[15];
+    p.pt = geom[16]; p.ph = geom[17]; p.pw = geom[18];
+    const int n_out = geom[19];
+    if ((p.cs & 7) || (p.cd & 3)) return selavi_fail(-1, "conv_dgrad_bf16: bad channel strides");
+    if (p.kt * p.kh * p.kw > DG_MAX_TAPS || p.kt > 8 || p.kh > 8 || p.kw > 8) return selavi_fail(-1, "conv_dgrad_bf16: kernel too large");
+    if ((p.st != 1 && p.st != 2) || (p.sh != 1 && p.sh != 2) || (p.sw != 1 && p.sw != 2)) return selavi_fail(-1, "conv_dgrad_bf16: stride must be 1 or 2");
+    if (passes != 1 && passes != 3) return selavi_fail(-1, "conv_dgrad_bf16: passes must be 1 or 3");
+    const long long M = (long long)p.nb * p.td * p.hd * p.wd;
+    if (M <= 0 || M > 0x7fffffffLL || (long long)p.nb * p.ts * p.hs * p.ws > 0x7fffffffLL) return selavi_fail(-1, "conv_dgrad_bf16: bad pixel count");
+    p.M = (int)M;
+    dg_tiles(n_out, &p.bnt, &p.ntiles);
+    if (p.ntiles * p.bnt < p.cd) return selavi_fail(-1, "conv_dgrad_bf16: cd exceeds the tiled channel range");
+    p.kstages = (p.kt * p.kh * p.kw * (p.cs >> 3) + 7) / 8;
+    p.m_tiles = (p.M + DG_BM - 1) / DG_BM;
+    p.accumulate = accumulate;
+    p.passes = passes;
+    uint32_t cols = 32;
+    while ((int)cols < 2 * p.bnt) cols <<= 1;
+    p.tmem_cols = cols;
+    const int stage_bytes = 2 * DG_A_BYTES + 2 * p.bnt * 128;
+    const int tail_bytes = (2 * DG_MAX_STAGES + 4) * 8 + 8 + 2 * DG_MAX_TAPS * 4 + 64;
+    int stages = (227 * 1024 - 1024 - tail_bytes) / stage_bytes;
+    if (stages > DG_MAX_STAGES) stages = DG_MAX_STAGES;
+    if (stages < 2) return selavi_fail(-1, "conv_dgrad_bf16: tile does not fit shared memory");
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + tail_bytes + 1024;
+    SV_CUDA_CHECK(cudaFuncSetAttribute(dgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                  "conv_dgrad_bf16: cudaFuncSetAttribute");
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int total_tiles = p.m_tiles * p.ntiles;
+    dgrad_bf16_kernel<<<total_tiles < sms ? total_tiles : sms, DG_THREADS, smem, (cudaStream_t)stream>>>(p);
+    SV_CUDA_CHECK(cudaGetLastError(), "conv_dgrad_bf16: launch");
+    return 0;
+}

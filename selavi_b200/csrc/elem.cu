@@ -6,6 +6,7 @@
 // for running_var, momentum 0.1, eps 1e-5; SyncBN path torch:nn/modules/_functions.py:39-200), the
 // BasicBlock residual add + ReLU (tv:video/resnet.py:107-119, tv:resnet.py:89-105), MaxPool2d(3,2,1)
 // (tv:resnet.py:271), AdaptiveAvgPool (tv:video/resnet.py:230), torch.optim.SGD (main.py:132-137).
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 #include "../../include/selavi_b200.h"
@@ -175,7 +176,7 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* 
                                     const float4* __restrict__ shift, const float4* __restrict__ mean,
                                     const float4* __restrict__ invstd, const double* __restrict__ sums, double count,
                                     long long total4, int c4n, float4* __restrict__ dz, float4* __restrict__ gres,
-                                    int gres_accumulate) {
+                                    int gres_accumulate, uint2* __restrict__ dz_hi, uint2* __restrict__ dz_lo) {
     const int cs = c4n * 4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
         const int c4 = (int)(i % c4n);
@@ -197,7 +198,14 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* 
         o.y = sc.y * (gg.y - m1y - (zz.y - mu.y) * is.y * m2y);
         o.z = sc.z * (gg.z - m1z - (zz.z - mu.z) * is.z * m2z);
         o.w = sc.w * (gg.w - m1w - (zz.w - mu.w) * is.w * m2w);
-        dz[i] = o;
+        if (dz) dz[i] = o;
+        if (dz_hi) {   // bf16 hi/lo planes for the bf16x3 data / weight gradient kernels
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+            const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - __low2float(h0), o.y - __high2float(h0));
+            const __nv_bfloat162 l1 = __floats2bfloat162_rn(o.z - __low2float(h1), o.w - __high2float(h1));
+            dz_hi[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+            dz_lo[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        }
         if (gres) {
             float4 r = gg;
             if (gres_accumulate) {
@@ -416,15 +424,17 @@ extern "C" int selavi_bn_bwd_reduce(const float* g, const float* z, const float*
 extern "C" int selavi_bn_bwd_apply(const float* g, const float* z, const float* act, int mask_mode, const float* scale,
                                    const float* shift, const float* mean, const float* invstd, const double* sums,
                                    double count, long long M, int cs, float* dz, float* gres, int gres_accumulate,
-                                   void* stream) {
-    if (!g || !z || !scale || !mean || !invstd || !sums || !dz || (cs & 3) || M <= 0 || count <= 0)
+                                   void* dz_hi, void* dz_lo, void* stream) {
+    if (!g || !z || !scale || !mean || !invstd || !sums || (!dz && !dz_hi) || (cs & 3) || M <= 0 || count <= 0 ||
+        ((dz_hi == nullptr) != (dz_lo == nullptr)))
         return selavi_fail(-1, "bn_bwd_apply: bad arguments");
     if (mask_mode == 1 && !act) return selavi_fail(-1, "bn_bwd_apply: mask_mode 1 needs act");
     if (mask_mode == 2 && !shift) return selavi_fail(-1, "bn_bwd_apply: mask_mode 2 needs shift");
     const long long total4 = M * (cs / 4);
     bn_bwd_apply_kernel<<<ew_blocks(total4), EW_THREADS, 0, (cudaStream_t)stream>>>(
         (const float4*)g, (const float4*)z, (const float4*)act, mask_mode, (const float4*)scale, (const float4*)shift,
-        (const float4*)mean, (const float4*)invstd, sums, count, total4, cs / 4, (float4*)dz, (float4*)gres, gres_accumulate);
+        (const float4*)mean, (const float4*)invstd, sums, count, total4, cs / 4, (float4*)dz, (float4*)gres, gres_accumulate,
+        (uint2*)dz_hi, (uint2*)dz_lo);
     LAUNCH_CHECK("bn_bwd_apply");
     return 0;
 }

@@ -640,12 +640,17 @@ extern "C" size_t selavi_wgrad_workspace_bytes(const int* geom) {
     return align256(partial) + 2 * align256((size_t)Min * geom[5] * 2) + 2 * align256((size_t)M * geom[9] * 2) + 256;
 }
 
-// geom: same 20 ints as selavi_conv_gemm with mode 0 (the FORWARD geometry of the convolution); dz is [M, cd].
-extern "C" int selavi_conv_wgrad(const float* src, const float* dz, float* dW, const int* geom, int ci_real,
-                                 const float* pro_scale, const float* pro_shift, int pro_relu, void* workspace,
-                                 int accumulate, int passes, void* stream_) {
-    if (!src || !dz || !dW || !geom || !workspace) return selavi_fail(-1, "conv_wgrad: null argument");
-    cudaStream_t stream = (cudaStream_t)stream_;
+namespace {
+
+int blocks_for(long long n) {
+    long long b = (n + 255) / 256;
+    return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
+}
+
+// Common driver.  z_hi/z_lo: pre-split bf16 dz (bf16 path) or null; dz: fp32 dz (tf32 path, or bf16 path without pre-split).
+int wgrad_run(const float* src, const float* dz, const void* z_hi_in, const void* z_lo_in, float* dW, const int* geom,
+              int ci_real, const float* pro_scale, const float* pro_shift, int pro_relu, void* workspace, int accumulate,
+              int passes, cudaStream_t stream) {
     WgradParams p;
     p.src = src;
     p.dz = dz;
@@ -672,6 +677,7 @@ extern "C" int selavi_conv_wgrad(const float* src, const float* dz, float* dW, c
     p.total_kstages = pl.total_kstages; p.kstages_per_slice = pl.kstages_per_slice;
     p.pro_relu = pro_relu;
     const bool bf16 = passes < 10;
+    if (!bf16 && !dz) return selavi_fail(-1, "conv_wgrad: the tf32 path needs the fp32 gradient");
     p.passes = bf16 ? passes : passes - 10;
     uint32_t cols = 32;
     while ((int)cols < p.bnt) cols <<= 1;
@@ -685,21 +691,26 @@ extern "C" int selavi_conv_wgrad(const float* src, const float* dz, float* dW, c
     const size_t smem = (size_t)stages * stage_bytes + tail_bytes + 1024;
     dim3 grid(pl.mtiles * pl.ntiles, pl.slices);
     if (bf16) {
-        // operand preparation: normalise + split the conv input, split dz (one HBM pass each)
+        // operand preparation: normalise + split the conv input (and dz unless it arrives pre-split): one HBM pass each
         const size_t partial_bytes = align256((size_t)pl.slices * pl.mtiles * 128 * pl.ntiles * pl.bnt * sizeof(float));
         unsigned char* w = reinterpret_cast<unsigned char*>(workspace) + partial_bytes;
         const size_t a_bytes = align256((size_t)Min * p.cs * 2), z_bytes = align256((size_t)M * p.cd * 2);
         WgradBf16Params q;
         q.a_hi = reinterpret_cast<const __nv_bfloat16*>(w);
         q.a_lo = reinterpret_cast<const __nv_bfloat16*>(w + a_bytes);
-        q.z_hi = reinterpret_cast<const __nv_bfloat16*>(w + 2 * a_bytes);
-        q.z_lo = reinterpret_cast<const __nv_bfloat16*>(w + 2 * a_bytes + z_bytes);
         const long long a4 = Min * (p.cs / 4), z4 = M * (p.cd / 4);
-        auto blocks = [](long long n) { long long b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); };
-        split_bf16_kernel<<<blocks(a4), 256, 0, stream>>>((const float4*)src, (const float4*)pro_scale, (const float4*)pro_shift,
-                                                          pro_relu, (uint2*)q.a_hi, (uint2*)q.a_lo, a4, p.cs / 4);
-        split_bf16_kernel<<<blocks(z4), 256, 0, stream>>>((const float4*)dz, nullptr, nullptr, 0, (uint2*)q.z_hi, (uint2*)q.z_lo,
-                                                          z4, p.cd / 4);
+        split_bf16_kernel<<<blocks_for(a4), 256, 0, stream>>>((const float4*)src, (const float4*)pro_scale, (const float4*)pro_shift,
+                                                              pro_relu, (uint2*)q.a_hi, (uint2*)q.a_lo, a4, p.cs / 4);
+        if (z_hi_in) {
+            q.z_hi = reinterpret_cast<const __nv_bfloat16*>(z_hi_in);
+            q.z_lo = reinterpret_cast<const __nv_bfloat16*>(z_lo_in);
+        } else {
+            if (!dz) return selavi_fail(-1, "conv_wgrad: no gradient given");
+            q.z_hi = reinterpret_cast<const __nv_bfloat16*>(w + 2 * a_bytes);
+            q.z_lo = reinterpret_cast<const __nv_bfloat16*>(w + 2 * a_bytes + z_bytes);
+            split_bf16_kernel<<<blocks_for(z4), 256, 0, stream>>>((const float4*)dz, nullptr, nullptr, 0, (uint2*)q.z_hi,
+                                                                  (uint2*)q.z_lo, z4, p.cd / 4);
+        }
         SV_CUDA_CHECK(cudaGetLastError(), "conv_wgrad: split launch");
         q.partial = p.partial;
         q.nb = p.nb; q.ts = p.ts; q.hs = p.hs; q.ws = p.ws; q.cs = p.cs;
@@ -720,8 +731,40 @@ extern "C" int selavi_conv_wgrad(const float* src, const float* dz, float* dW, c
     const size_t total = (size_t)co * ci_real * taps;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, pl.slices, pl.mtiles * 128, pl.ntiles * pl.bnt,
-                                                                  co, ci_real, taps, p.cs, dW, accumulate);
+    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, pl.slices, pl.mtiles * 128, pl.ntiles * pl.bnt, co, ci_real, taps,
+                                                    p.cs, dW, accumulate);
     SV_CUDA_CHECK(cudaGetLastError(), "conv_wgrad: reduce launch");
+    return 0;
+}
+
+}  // namespace
+
+// geom: same 20 ints as selavi_conv_gemm with mode 0 (the FORWARD geometry of the convolution); dz is [M, cd].
+extern "C" int selavi_conv_wgrad(const float* src, const float* dz, float* dW, const int* geom, int ci_real,
+                                 const float* pro_scale, const float* pro_shift, int pro_relu, void* workspace,
+                                 int accumulate, int passes, void* stream) {
+    if (!src || !dz || !dW || !geom || !workspace) return selavi_fail(-1, "conv_wgrad: null argument");
+    return wgrad_run(src, dz, nullptr, nullptr, dW, geom, ci_real, pro_scale, pro_shift, pro_relu, workspace, accumulate, passes,
+                     (cudaStream_t)stream);
+}
+
+// same, with the gradient already split into bf16 hi/lo planes [M, cd] (written by selavi_bn_bwd_apply / selavi_split_bf16)
+extern "C" int selavi_conv_wgrad_bf16(const float* src, const void* z_hi, const void* z_lo, float* dW, const int* geom,
+                                      int ci_real, const float* pro_scale, const float* pro_shift, int pro_relu,
+                                      void* workspace, int accumulate, int passes, void* stream) {
+    if (!src || !z_hi || !z_lo || !dW || !geom || !workspace) return selavi_fail(-1, "conv_wgrad_bf16: null argument");
+    if (passes != 1 && passes != 3) return selavi_fail(-1, "conv_wgrad_bf16: passes must be 1 or 3");
+    return wgrad_run(src, nullptr, z_hi, z_lo, dW, geom, ci_real, pro_scale, pro_shift, pro_relu, workspace, accumulate, passes,
+                     (cudaStream_t)stream);
+}
+
+// x [M, cs] fp32 -> bf16 hi/lo planes, optional fused affine (+ReLU):  hi = bf16(y), lo = bf16(y - hi), y = act(x*scale+shift)
+extern "C" int selavi_split_bf16(const float* x, const float* scale, const float* shift, int relu, void* hi, void* lo,
+                                 long long M, int cs, void* stream) {
+    if (!x || !hi || !lo || M <= 0 || (cs & 3) || ((scale == nullptr) != (shift == nullptr))) return selavi_fail(-1, "split_bf16: bad arguments");
+    const long long n4 = M * (cs / 4);
+    split_bf16_kernel<<<blocks_for(n4), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)scale, (const float4*)shift,
+                                                                       relu, (uint2*)hi, (uint2*)lo, n4, cs / 4);
+    SV_CUDA_CHECK(cudaGetLastError(), "split_bf16: launch");
     return 0;
 }

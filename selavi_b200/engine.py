@@ -21,6 +21,9 @@ from . import _lib, ops
 
 # tf32x3 split (fp32-class accuracy) is the parity mode; SELAVI_MMA_PASSES=1 selects single-pass tf32 (fast mode).
 PASSES = int(os.environ.get("SELAVI_MMA_PASSES", "3"))
+# backward (data + weight gradients): "bf16x3" (default; gradient planes written as bf16 hi/lo by the BN-backward
+# kernel, cp.async-fed tcgen05 kind::f16 kernels, measured 4e-6 per-layer error) or "tf32x3" (register-staged loaders)
+BWD = os.environ.get("SELAVI_BWD", "bf16x3")
 
 
 def _stream():
@@ -49,6 +52,18 @@ class Act:
 class ConvRec:
     """Everything the backward pass needs about one conv+BN unit."""
     __slots__ = ("conv", "bn", "geom", "inp", "z", "scale", "shift", "mean", "invstd", "count")
+
+
+def _packed_dgrad_bf16(conv, geom):
+    weight = conv.weight
+    cache = conv.__dict__.setdefault("_sv_pack", {})
+    tag = (weight.data_ptr(), weight._version)
+    hit = cache.get("dgrad_bf16")
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    buf = ops.pack_weights_dgrad_bf16(weight, geom, out=hit[1] if (hit is not None and hit[1].device == weight.device) else None)
+    cache["dgrad_bf16"] = (tag, buf)
+    return buf
 
 
 def _packed(conv, geom, mode):
@@ -228,18 +243,33 @@ class TowerRunner:
         if _world(bn) > 1:
             sums = sums.clone()
             _allreduce(sums, bn)
-        dz = torch.empty_like(z)
+        bf16 = BWD == "bf16x3"
+        conv, inp = rec.conv, rec.inp
+        need_dw = conv.weight.requires_grad
+        dz = z_hi = z_lo = None
+        if bf16:
+            z_hi = torch.empty(z.shape, dtype=torch.bfloat16, device=dev)
+            z_lo = torch.empty(z.shape, dtype=torch.bfloat16, device=dev)
+        else:
+            dz = torch.empty_like(z)
         _lib.check(lib.selavi_bn_bwd_apply(_lib.ptr(g), _lib.ptr(z), _lib.ptr(act_mask), mask_mode, _lib.ptr(rec.scale),
                                            _lib.ptr(rec.shift), _lib.ptr(rec.mean), _lib.ptr(rec.invstd), _lib.ptr(sums),
                                            rec.count, M, cs, _lib.ptr(dz), _lib.ptr(gres), 1 if gres_accumulate else 0,
-                                           _stream()), "selavi_bn_bwd_apply")
-        conv, inp = rec.conv, rec.inp
-        if conv.weight.requires_grad:
+                                           _lib.ptr(z_hi), _lib.ptr(z_lo), _stream()), "selavi_bn_bwd_apply")
+        if need_dw:
             dw = torch.empty_like(conv.weight)
-            ops.conv_wgrad(inp.t, dz, geom, dw, scale=inp.scale, shift=inp.shift, relu=inp.relu, passes=PASSES)
+            if bf16:
+                ops.conv_wgrad_bf16(inp.t, z_hi, z_lo, geom, dw, scale=inp.scale, shift=inp.shift, relu=inp.relu,
+                                    passes=3 if PASSES == 3 else 1)
+            else:
+                ops.conv_wgrad(inp.t, dz, geom, dw, scale=inp.scale, shift=inp.shift, relu=inp.relu,
+                               passes=13 if PASSES == 3 else 11)
             grads[conv.weight] = dw
         if not want_dx:
             return None
+        if bf16:
+            return ops.conv_dgrad_bf16(z_hi, z_lo, _packed_dgrad_bf16(conv, geom), geom, out=dx_out, accumulate=dx_accumulate,
+                                       passes=3 if PASSES == 3 else 1)
         wpt = _packed(conv, geom, 1)
         return ops.conv_dgrad(dz, wpt, geom, out=dx_out, accumulate=dx_accumulate, passes=PASSES)
 

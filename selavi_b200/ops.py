@@ -169,3 +169,73 @@ def conv_wgrad(x, dz, geom, dw, scale=None, shift=None, relu=False, accumulate=F
                                          _lib.ptr(shift), 1 if relu else 0, _lib.ptr(ws), 1 if accumulate else 0, passes,
                                          _lib.stream_ptr()), "selavi_conv_wgrad")
     return dw
+
+
+# ---------------------------------------------------------------------------------------------- bf16x3 backward
+def split_bf16(x, scale=None, shift=None, relu=False):
+    """fp32 [.., Cs] -> (hi, lo) bf16 planes of act(x*scale+shift); hi = bf16(y), lo = bf16(y - hi)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+        raise ValueError("split_bf16 needs a contiguous fp32 CUDA tensor")
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().selavi_split_bf16(_lib.ptr(x), _lib.ptr(scale), _lib.ptr(shift), 1 if relu else 0, _lib.ptr(hi),
+                                                _lib.ptr(lo), x.numel() // x.shape[-1], x.shape[-1], _lib.stream_ptr()),
+                   "selavi_split_bf16")
+    return hi, lo
+
+
+def pack_weights_dgrad_bf16(w, geom, out=None):
+    """torch weight [co, ci, taps...] -> bf16 hi/lo B operand of the data gradient (n = ci, k = (tap, co))."""
+    w = w.detach()
+    if not (w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()):
+        raise ValueError("weight must be a contiguous fp32 CUDA tensor")
+    lib = _lib.lib()
+    nbytes = lib.selavi_dgrad_wpack_bytes(geom.ci, geom.taps * geom.cos)
+    if out is None:
+        out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    elif out.numel() != nbytes:
+        raise ValueError("packed weight buffer has the wrong size")
+    with torch.cuda.device(w.device):
+        _lib.check(lib.selavi_dgrad_pack_weights(_lib.ptr(w), geom.co, geom.ci, geom.taps, geom.cos, _lib.ptr(out),
+                                                 _lib.stream_ptr()), "selavi_dgrad_pack_weights")
+    return out
+
+
+def _chk_bf16(t, shape, name):
+    if not (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous() and tuple(t.shape) == tuple(shape)):
+        raise ValueError(f"{name}: expected contiguous bf16 CUDA tensor of shape {tuple(shape)}")
+
+
+def conv_dgrad_bf16(z_hi, z_lo, wpack_bf16, geom, out=None, accumulate=False, passes=3):
+    _chk_bf16(z_hi, geom.out_shape(), "z_hi")
+    _chk_bf16(z_lo, geom.out_shape(), "z_lo")
+    if out is None:
+        out = torch.empty(geom.in_shape(), dtype=torch.float32, device=z_hi.device)
+        accumulate = False
+    _chk(out, geom.in_shape(), "dx")
+    with torch.cuda.device(z_hi.device), _Prof("conv_dgrad", geom):
+        _lib.check(_lib.lib().selavi_conv_dgrad_bf16(_lib.ptr(z_hi), _lib.ptr(z_lo), _lib.ptr(out), _lib.ptr(wpack_bf16),
+                                                     geom.arr(1), 1 if accumulate else 0, passes, _lib.stream_ptr()),
+                   "selavi_conv_dgrad_bf16")
+    return out
+
+
+def conv_wgrad_bf16(x, z_hi, z_lo, geom, dw, scale=None, shift=None, relu=False, accumulate=False, passes=3):
+    _chk(x, geom.in_shape(), "x")
+    _chk_bf16(z_hi, geom.out_shape(), "z_hi")
+    _chk_bf16(z_lo, geom.out_shape(), "z_lo")
+    if not (dw.is_cuda and dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == geom.co * geom.ci * geom.taps):
+        raise ValueError("dw must be a contiguous fp32 CUDA tensor in the torch weight layout")
+    lib = _lib.lib()
+    nbytes = lib.selavi_wgrad_workspace_bytes(geom.arr(0))
+    key = (x.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _wgrad_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _wgrad_ws[key] = ws
+    with torch.cuda.device(x.device), _Prof("conv_wgrad", geom):
+        _lib.check(lib.selavi_conv_wgrad_bf16(_lib.ptr(x), _lib.ptr(z_hi), _lib.ptr(z_lo), _lib.ptr(dw), geom.arr(0), geom.ci,
+                                              _lib.ptr(scale), _lib.ptr(shift), 1 if relu else 0, _lib.ptr(ws),
+                                              1 if accumulate else 0, passes, _lib.stream_ptr()), "selavi_conv_wgrad_bf16")
+    return dw

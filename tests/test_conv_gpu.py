@@ -108,3 +108,29 @@ def test_conv_wgrad(cuda_device, name, passes):
     err = _rel(dw, ref_dw)
     print(f"{name} wgrad passes={passes} rel={err:.3e}")
     assert err < 5e-5
+
+
+@pytest.mark.parametrize("name", sorted(LAYERS))
+def test_conv_dgrad_bf16x3(cuda_device, name):
+    """data gradient on pre-split bf16 hi/lo planes (cp.async-fed kind::f16 kernel), tolerance 5e-5 like tf32x3"""
+    from selavi_b200 import ops
+    x, w, geom, (s, p) = _mk(name, cuda_device)
+    xd = x.double().requires_grad_(True)
+    ref_y = F.conv3d(xd, w.double(), None, s, p)
+    dz = torch.randn(ref_y.shape, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(7))
+    ref_dx, = torch.autograd.grad(ref_y, xd, dz.double())
+    z_hi, z_lo = ops.split_bf16(ops.to_channels_last(dz))
+    torch.testing.assert_close(z_hi.float() + z_lo.float(), ops.to_channels_last(dz), rtol=2e-5, atol=1e-30)
+    wp = ops.pack_weights_dgrad_bf16(w, geom)
+    dx = ops.conv_dgrad_bf16(z_hi, z_lo, wp, geom)
+    err = _rel(ops.from_channels_last(dx, geom.ci), ref_dx)
+    print(f"{name} dgrad bf16x3 rel={err:.3e}")
+    assert err < 5e-5
+    dx2 = ops.conv_dgrad_bf16(z_hi, z_lo, wp, geom, out=dx.clone(), accumulate=True)
+    assert _rel(dx2, 2 * dx) < 1e-6
+    # wgrad on the same pre-split planes
+    wd = w.double().requires_grad_(True)
+    ref_dw, = torch.autograd.grad(F.conv3d(x.double(), wd, None, s, p), wd, dz.double())
+    dw = torch.empty_like(w)
+    ops.conv_wgrad_bf16(ops.to_channels_last(x), z_hi, z_lo, geom, dw)
+    assert _rel(dw, ref_dw) < 5e-5

@@ -13,6 +13,7 @@ CHECKS = [
     ("conv_fwd_pro", "tests/test_conv_gpu.py::test_conv_forward_fused_bn_relu_prologue_and_stats"),
     ("conv_dgrad", "tests/test_conv_gpu.py::test_conv_dgrad"),
     ("conv_wgrad", "tests/test_conv_gpu.py::test_conv_wgrad"),
+    ("conv_bf16bwd", "tests/test_conv_gpu.py::test_conv_dgrad_bf16x3"),
     ("heads", "tests/test_model_gpu.py::test_heads_linear_and_dropout_paths"),
     ("ce", "tests/test_model_gpu.py::test_ce_loss_matches_torch"),
     ("sgd", "tests/test_model_gpu.py::test_sgd_matches_torch"),

@@ -53,8 +53,13 @@ def bench_conv(name, nb, ci, co, thw, k, s, p):
         ms = timeit(lambda: ops.conv_forward(x, wp, geom, out=y, stats=stats, passes=passes))
         msd = timeit(lambda: ops.conv_dgrad(dz, wpt, geom, out=dx, passes=passes))
         msw = timeit(lambda: ops.conv_wgrad(x, dz, geom, dw, passes=passes))
+        z_hi, z_lo = ops.split_bf16(dz)
+        wpb = ops.pack_weights_dgrad_bf16(w, geom)
+        msdb = timeit(lambda: ops.conv_dgrad_bf16(z_hi, z_lo, wpb, geom, out=dx, passes=passes))
+        mswb = timeit(lambda: ops.conv_wgrad_bf16(x, z_hi, z_lo, geom, dw, passes=passes))
         print(f"{name} passes={passes}: fwd {ms:.3f} ms ({flop / ms / 1e9:.1f} TF/s)  dgrad {msd:.3f} ms ({flop / msd / 1e9:.1f})"
-              f"  wgrad {msw:.3f} ms ({flop / msw / 1e9:.1f})", flush=True)
+              f"  wgrad {msw:.3f} ms ({flop / msw / 1e9:.1f}) | bf16 presplit: dgrad {msdb:.3f} ms ({flop / msdb / 1e9:.1f})"
+              f"  wgrad {mswb:.3f} ms ({flop / mswb / 1e9:.1f})", flush=True)
 
 
 if __name__ == "__main__":
