@@ -36,8 +36,9 @@ const char* selavi_last_error(void);
  * do_prep     1: pow + marginals + initial sums (a fresh solve).  0: PS already powered, continue from the
  *             state left in `workspace` by the previous call (used by the iteration micro-benchmark).
  * world/rank  rows sharded over `world` GPUs; peer_sum[r] / peer_flag[r] are P2P-mapped symmetric
- *             buffers (selavi_symm_*) of 2*selavi_sk_kp(K) doubles / 1 uint32 per rank; the flag word
- *             must be zero on every rank when the call starts.  world == 1: pass NULL.
+ *             buffers (selavi_symm_*) of 2*world*selavi_sk_kp(K) doubles / world uint32 per rank (receive slots
+ *             and flags, one per source rank); the flag words must be zero on every rank when the call
+ *             starts.  world == 1: pass NULL.
  * Replaces the NCCL all-gather + rank-0 solve of src/sk_utils.py:214-242,287-327.
  */
 /* PS[n,k] = softmax_f64(logits_v[n,:])[k] * softmax_f64(logits_a[n,:])[k]  (src/sk_utils.py:206-211,309-315) */
@@ -189,6 +190,13 @@ int selavi_symm_open(const unsigned char* handle64, void** ptr_out);
 int selavi_symm_close(void* ptr);
 int selavi_symm_free(void* ptr);
 int selavi_symm_memset(void* ptr, int value, size_t bytes, void* stream);
+/* In-place sum all-reduce of data[n] (float64, n small) over peer memory, one CTA, push model — replaces the NCCL
+ * collectives of SyncBatchNorm (torch:nn/modules/_functions.py:49-117,144-200).  peer_recv[r] / peer_flag[r]: rank r's
+ * receive ring (doubles) and flag array (uint64, zero-initialised); every rank issues the same sequence of calls with
+ * the same slot_off (ring offset in doubles; the call uses world*n doubles from there), flag_idx and seqval
+ * (strictly increasing, > 0). */
+int selavi_p2p_allreduce_f64(double* data, int n, int world, int rank, void* const* peer_recv, void* const* peer_flag,
+                             long long slot_off, int flag_idx, long long seqval, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Diagnostics: issue n_mma tcgen05.mma instructions (kind 0 = tf32, 1 = f16/bf16) on host-provided raw shared-memory operand

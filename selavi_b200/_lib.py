@@ -88,6 +88,7 @@ SIGNATURES = {
     "selavi_symm_close": (c_int, [c_void_p]),
     "selavi_symm_free": (c_int, [c_void_p]),
     "selavi_symm_memset": (c_int, [c_void_p, c_int, c_size_t, c_void_p]),
+    "selavi_p2p_allreduce_f64": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_ll, c_int, c_ll, c_void_p]),
 }
 
 
@@ -104,7 +105,7 @@ KERNELS_PER_CALL = {
     "selavi_sgd_step": 1, "selavi_bgemm": 1, "selavi_heads_bn_stats": 1, "selavi_heads_bn_finalize": 1,
     "selavi_heads_bn_eval_affine": 1, "selavi_heads_act": 1, "selavi_heads_bn_bwd_reduce": 1,
     "selavi_heads_bn_bwd_apply": 1, "selavi_heads_sum_masked": 1, "selavi_heads_colsum": 1, "selavi_ce_loss": 2,
-    "selavi_debug_umma_probe": 1, "selavi_mel_logfbank": 1, "selavi_split_bf16": 1, "selavi_conv_wgrad_bf16": 3,
+    "selavi_debug_umma_probe": 1, "selavi_mel_logfbank": 1, "selavi_split_bf16": 1, "selavi_p2p_allreduce_f64": 1, "selavi_conv_wgrad_bf16": 3,
     "selavi_dgrad_pack_weights": 1, "selavi_conv_dgrad_bf16": 1,
 }
 COUNT_CALLS = False

@@ -23,21 +23,47 @@ inline int ew_blocks(long long n) {
 }
 
 // ---------------------------------------------------------------- stats: partial tiles -> fp64 sums
-// partial [tiles][2][ctot] fp32 -> sums [2][cs] fp64 (fixed order; channels >= ctot are zero)
+// partial [tiles][2][ctot] fp32 -> sums [2][cs] fp64 (fixed order; channels >= ctot are zero).
+// grid (ceil(cs/32), 2, nchunk): every z-chunk reduces a contiguous range of tiles into scratch[chunk][2][cs]; the block
+// that finishes last (atomic ticket) adds the chunks in chunk order => deterministic, and ~nchunk x more parallel than
+// a single pass (12 544 tiles for the layer-1 convolutions).
+constexpr int RP_MAX_CHUNKS = 16;
+constexpr int RP_MAX_CS = 2048;
+
 __global__ void bn_reduce_partials_kernel(const float* __restrict__ partial, int tiles, int ctot, int cs,
-                                          double* __restrict__ sums) {
+                                          double* __restrict__ sums, double* __restrict__ scratch, unsigned* __restrict__ tickets) {
     __shared__ double red[32][33];
+    __shared__ bool is_last;
     const int c = blockIdx.x * 32 + threadIdx.x;
     const int which = blockIdx.y;
+    const int nchunk = gridDim.z, chunk = blockIdx.z;
+    const int per = (tiles + nchunk - 1) / nchunk;
+    const int t0 = chunk * per, t1 = min(tiles, t0 + per);
     double s = 0.0;
     if (c < ctot && c < cs) {
-        for (int t = threadIdx.y; t < tiles; t += 32) s += (double)partial[((size_t)t * 2 + which) * ctot + c];
+        for (int t = t0 + threadIdx.y; t < t1; t += 32) s += (double)partial[((size_t)t * 2 + which) * ctot + c];
     }
     red[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && c < cs) {
         double tot = 0.0;
         for (int i = 0; i < 32; ++i) tot += red[i][threadIdx.x];
+        if (nchunk == 1) sums[(size_t)which * cs + c] = tot;
+        else scratch[((size_t)chunk * 2 + which) * RP_MAX_CS + c] = tot;
+    }
+    if (nchunk == 1) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const unsigned prev = atomicAdd(&tickets[blockIdx.y * gridDim.x + blockIdx.x], 1u);
+        is_last = (prev == (unsigned)nchunk - 1);
+        if (is_last) tickets[blockIdx.y * gridDim.x + blockIdx.x] = 0;   // re-arm for the next launch
+    }
+    __syncthreads();
+    if (is_last && threadIdx.y == 0 && c < cs) {
+        __threadfence();
+        double tot = 0.0;
+        for (int k = 0; k < nchunk; ++k) tot += scratch[((size_t)k * 2 + which) * RP_MAX_CS + c];
         sums[(size_t)which * cs + c] = tot;
     }
 }
@@ -357,10 +383,28 @@ __global__ void sgd_kernel(const SgdEntry* __restrict__ table, int n_tensors, fl
 
 #define LAUNCH_CHECK(what) SV_CUDA_CHECK(cudaGetLastError(), what)
 
+namespace {
+// per-device scratch of the chunked reduction (stream-ordered use only: one reduction in flight per device)
+double* g_rp_scratch[16] = {nullptr};
+unsigned* g_rp_tickets[16] = {nullptr};
+}
+
 extern "C" int selavi_bn_reduce_partials(const float* partial, int tiles, int ctot, int cs, double* sums, void* stream) {
-    if (!partial || !sums || tiles <= 0 || cs <= 0) return selavi_fail(-1, "bn_reduce_partials: bad arguments");
-    dim3 grid((cs + 31) / 32, 2), block(32, 32);
-    bn_reduce_partials_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(partial, tiles, ctot, cs, sums);
+    if (!partial || !sums || tiles <= 0 || cs <= 0 || cs > RP_MAX_CS) return selavi_fail(-1, "bn_reduce_partials: bad arguments");
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) return selavi_fail(-1, "bn_reduce_partials: device index out of range");
+    if (!g_rp_scratch[dev]) {
+        SV_CUDA_CHECK(cudaMalloc(&g_rp_scratch[dev], sizeof(double) * RP_MAX_CHUNKS * 2 * RP_MAX_CS), "bn_reduce_partials: scratch");
+        SV_CUDA_CHECK(cudaMalloc(&g_rp_tickets[dev], sizeof(unsigned) * 2 * (RP_MAX_CS / 32)), "bn_reduce_partials: tickets");
+        SV_CUDA_CHECK(cudaMemset(g_rp_tickets[dev], 0, sizeof(unsigned) * 2 * (RP_MAX_CS / 32)), "bn_reduce_partials: tickets");
+    }
+    int nchunk = tiles / 256;
+    if (nchunk < 1) nchunk = 1;
+    if (nchunk > RP_MAX_CHUNKS) nchunk = RP_MAX_CHUNKS;
+    dim3 grid((cs + 31) / 32, 2, nchunk), block(32, 32);
+    bn_reduce_partials_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(partial, tiles, ctot, cs, sums, g_rp_scratch[dev],
+                                                                        g_rp_tickets[dev]);
     LAUNCH_CHECK("bn_reduce_partials");
     return 0;
 }

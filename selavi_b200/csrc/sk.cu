@@ -15,10 +15,10 @@
 // the 126 MB L2.  Convergence (err = sum |beta/beta' - 1| every `check_every` iterations) is decided
 // on-device with the reference's exact stopping rule; no host sync inside the loop.
 //
-// Multi-GPU (rows sharded over ranks): `peer_sum[r]` point at every rank's exchange buffer (NVSwitch
-// P2P-mapped memory); once per iteration CTA 0 of every rank publishes its reduced [colsum.., err]
-// vector there and every CTA of every rank reads all peers' vectors over NVLink in rank order
-// (same summation order everywhere => identical alpha on all ranks).  Flags in peer memory order it.
+// Multi-GPU (rows sharded over ranks): `peer_sum[r]` point at every rank's receive buffer (NVSwitch
+// P2P-mapped memory); once per iteration CTA 0 of every rank PUSHES its reduced [colsum.., err] vector
+// into its slot of every rank's buffer (posted stores over NVLink) and raises a flag there; all CTAs poll
+// and sum LOCAL memory in rank order (same summation order everywhere => identical alpha on all ranks).
 #include <math.h>
 #include <stdint.h>
 
@@ -62,8 +62,8 @@ struct SkArgs {
     double* cost_out;  // local nansum(log PS[n,L_n]) contribution (host divides)
     int world;
     int rank;
-    double* peer_sum[SK_MAX_WORLD];     // [2][Ks]  each rank's reduced vector
-    unsigned* peer_flag[SK_MAX_WORLD];  // [1] epoch flag (zeroed by the host before the call, all ranks)
+    double* peer_sum[SK_MAX_WORLD];     // [2][world][Ks]  receive slots of each rank (slot r written by rank r)
+    unsigned* peer_flag[SK_MAX_WORLD];  // [world] epoch flags of each rank (zeroed by the host before the call)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -189,26 +189,31 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sk_kernel(const SkArgs a) {
         __syncthreads();
     };
 
-    // Cross-GPU all-reduce of vec[Ks] (smem), summed in rank order on every CTA of every rank.
+    // Cross-GPU all-reduce of vec[Ks] (smem), summed in rank order on every CTA of every rank (identical alpha
+    // everywhere).  PUSH model: CTA 0 of rank r stores its vector into slot r of EVERY rank's receive buffer over
+    // NVSwitch (posted stores, one-way latency) and then raises flag r there; consumers poll and read LOCAL memory only.
     auto cross_gpu_sum = [&](double* vec) {
         if (a.world <= 1) return;
         xepoch += 1;
         const int buf = xepoch & 1;
         if (cta == 0) {
-            double* mine = a.peer_sum[a.rank] + (size_t)buf * Ks;
-            for (int k = tid; k < Ks; k += SK_THREADS) mine[k] = vec[k];
+            for (int idx = tid; idx < a.world * Ks; idx += SK_THREADS) {
+                const int pr = idx / Ks, k = idx - pr * Ks;
+                a.peer_sum[pr][(size_t)(buf * a.world + a.rank) * Ks + k] = vec[k];
+            }
             __threadfence_system();
             __syncthreads();
-            if (tid == 0) st_release_sys_u32(a.peer_flag[a.rank], xepoch);
+            if (tid < a.world) st_release_sys_u32(a.peer_flag[tid] + a.rank, xepoch);
         }
         if (tid < a.world) {
-            while (ld_acquire_sys_u32(a.peer_flag[tid]) < xepoch) {
+            while (ld_acquire_sys_u32(a.peer_flag[a.rank] + tid) < xepoch) {
             }
         }
         __syncthreads();
+        const double* mine = a.peer_sum[a.rank] + (size_t)buf * a.world * Ks;
         for (int k = tid; k < Ks; k += SK_THREADS) {
             double s = 0.0;
-            for (int r = 0; r < a.world; ++r) s += ld_volatile_f64(a.peer_sum[r] + (size_t)buf * Ks + k);
+            for (int r = 0; r < a.world; ++r) s += ld_volatile_f64(mine + (size_t)r * Ks + k);
             vec[k] = s;
         }
         __syncthreads();

@@ -37,8 +37,28 @@ def _world(bn):
     return 1
 
 
+# cross-rank exchange of the SyncBN statistic vectors: "p2p" = one tiny kernel over NVSwitch peer memory (default inside
+# one node, world <= 8), "nccl" = torch.distributed.all_reduce
+BN_EXCHANGE = os.environ.get("SELAVI_BN_EXCHANGE", "p2p")
+_p2p = {}
+
+
 def _allreduce(t, bn):
-    dist.all_reduce(t, group=bn.process_group)
+    group = bn.process_group
+    if BN_EXCHANGE == "p2p":
+        key = id(group)
+        ar = _p2p.get(key)
+        if ar is None:
+            from .symm import P2PAllReduce
+            try:
+                ar = P2PAllReduce(group)
+            except _lib.SelaviError:
+                ar = False
+            _p2p[key] = ar
+        if ar:
+            ar.allreduce_(t.view(-1))
+            return
+    dist.all_reduce(t, group=group)
 
 
 class Act:

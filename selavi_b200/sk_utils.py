@@ -117,8 +117,8 @@ class SKComm:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         ks = _lib.lib().selavi_sk_kp(K)
-        self.sum = SymmetricBuffer(2 * ks * 8, group)
-        self.flag = SymmetricBuffer(256, group)
+        self.sum = SymmetricBuffer(2 * self.world * ks * 8, group)   # [2][world][Ks] receive slots
+        self.flag = SymmetricBuffer(256, group)                       # [world] epoch flags
 
     def reset(self):
         """Zero the epoch flag on every rank before a solve (the kernel counts epochs from 0)."""

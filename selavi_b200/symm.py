@@ -48,3 +48,40 @@ class SymmetricBuffer:
             torch.cuda.synchronize()
             lib.selavi_symm_free(self._local)
             self._local = ctypes.c_void_p()
+
+
+class P2PAllReduce:
+    """Sum all-reduce of small float64 vectors through peer-mapped rings (one tiny kernel, no NCCL): the SyncBatchNorm
+    statistic exchange.  Every rank must issue the same sequence of calls (it does: same program, same layer order)."""
+    RING_DOUBLES = 4 << 20       # 32 MB receive ring per rank
+    FLAGS = 8192
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 8:
+            raise _lib.SelaviError("P2PAllReduce supports one NVSwitch domain (world <= 8)")
+        self.recv = SymmetricBuffer(self.RING_DOUBLES * 8, group)
+        self.flag = SymmetricBuffer(self.FLAGS * self.world * 8, group)
+        self._recv_arr = (ctypes.c_void_p * self.world)(*self.recv.peer_ptrs)
+        self._flag_arr = (ctypes.c_void_p * self.world)(*self.flag.peer_ptrs)
+        self.seq = 0
+        self.off = 0
+
+    def allreduce_(self, t):
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+            raise ValueError("P2PAllReduce needs a contiguous float64 CUDA tensor")
+        n = t.numel()
+        need = self.world * n
+        if need > self.RING_DOUBLES // 4:
+            raise ValueError("vector too large for the peer ring")
+        if self.off + need > self.RING_DOUBLES:
+            self.off = 0
+        self.seq += 1
+        _lib.check(_lib.lib().selavi_p2p_allreduce_f64(_lib.ptr(t), n, self.world, self.rank, self._recv_arr, self._flag_arr,
+                                                       self.off, self.seq % self.FLAGS, self.seq, _lib.stream_ptr()),
+                   "selavi_p2p_allreduce_f64")
+        self.off += need
+        return t
