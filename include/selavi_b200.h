@@ -138,6 +138,10 @@ int selavi_nchw_to_cl(const float* x, float* out, int nb, int C, long long P, in
 /* fused multi-tensor torch.optim.SGD step (main.py:132-137,302); table = device array of {p, g, buf, n} */
 int selavi_sgd_step(const void* table, int n_tensors, float lr, float momentum, float weight_decay, int first_step,
                     void* stream);
+/* same update, tensors given by HOST arrays of device pointers (passed to the kernels by value, 48 per launch): no
+ * device-side table, hence no host-to-device copy / synchronisation when gradient buffers move between steps */
+int selavi_sgd_step_host(void* const* params, void* const* grads, void* const* bufs, const long long* sizes, int n_tensors,
+                         float lr, float momentum, float weight_decay, int first_step, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Projection heads (model.py:62-90 MLPv2 / nn.Linear heads, model.py:201-252) and cross-entropy
@@ -146,7 +150,8 @@ int selavi_sgd_step(const void* table, int n_tensors, float lr, float momentum, 
  *   bgemm: C[h](m,n) (+)= sum_k A[h](m,k)*Amask[h](m,k)*B[h](k,n) + bias[h](n), arbitrary element strides.
  *   heads_bn_*: BatchNorm1d over the batch rows of z [H,B,F] (train: batch stats / eval: running stats),
  *               heads_act: a = relu(z*scale+shift)*mask (mask = dropout mask/(1-p) or NULL).
- *   ce_loss: loss_rows[h,b] = logsumexp(x) - x[label[b,h]], loss_mean = mean over (h,b) = get_loss();
+ *   ce_loss: logits of head h at logit_tbl[h] (device pointer table) or, when logit_tbl is NULL, at
+ *            logits_base + h*head_stride; loss_rows[h,b] = logsumexp(x) - x[label[b,h]], loss_mean = mean over (h,b) = get_loss();
  *            dlogits [H,B,K] = (softmax - onehot) * grad_scale (nullable).
  */
 int selavi_bgemm(int H, int M, int N, int K, const float* A, const void* const* A_tbl, long long a_bs, long long a_sm,
@@ -169,8 +174,9 @@ int selavi_heads_bn_bwd_apply(const float* da, const float* mask, const float* z
                               float* dz, void* stream);
 int selavi_heads_sum_masked(const float* x, const float* mask, float* out, int H, long long BF, int accumulate, void* stream);
 int selavi_heads_colsum(const float* x, float* out, int H, int M, int N, void* stream);
-int selavi_ce_loss(const void* const* logit_tbl, const long long* labels, long long lab_stride_b, long long lab_stride_h,
-                   int H, int B, int K, float grad_scale, float* loss_rows, float* loss_mean, float* dlogits, void* stream);
+int selavi_ce_loss(const void* const* logit_tbl, const float* logits_base, long long head_stride, const long long* labels,
+                   long long lab_stride_b, long long lab_stride_h, int H, int B, int K, float grad_scale, float* loss_rows,
+                   float* loss_mean, float* dlogits, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Mel-spectrogram front end (datasets/audio_utils.py:47-63 -> python_speech_features.logfbank): pre-emphasis,

@@ -77,8 +77,9 @@ SIGNATURES = {
                                           c_double, c_int, c_int, c_int, c_void_p, c_void_p]),
     "selavi_heads_sum_masked": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p]),
     "selavi_heads_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "selavi_ce_loss": (c_int, [c_void_p, c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
-                               c_void_p]),
+    "selavi_ce_loss": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
+    "selavi_sgd_step_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_int, c_void_p]),
     "selavi_mel_logfbank": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p, c_int, c_int, c_double, c_int,
                                     c_void_p, c_void_p]),
     "selavi_debug_umma_probe": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.c_ulonglong, ctypes.c_ulonglong,
@@ -102,7 +103,7 @@ KERNELS_PER_CALL = {
     "selavi_bn_reduce_partials": 1, "selavi_bn_finalize": 1, "selavi_bn_eval_affine": 1, "selavi_bn_apply": 1,
     "selavi_bn_bwd_reduce": 2, "selavi_bn_bwd_apply": 1, "selavi_relu_bwd": 1, "selavi_maxpool3x3s2_fwd": 1,
     "selavi_maxpool3x3s2_bwd": 1, "selavi_avgpool_fwd": 1, "selavi_avgpool_bwd": 1, "selavi_nchw_to_cl": 1,
-    "selavi_sgd_step": 1, "selavi_bgemm": 1, "selavi_heads_bn_stats": 1, "selavi_heads_bn_finalize": 1,
+    "selavi_sgd_step": 1, "selavi_sgd_step_host": 6, "selavi_bgemm": 1, "selavi_heads_bn_stats": 1, "selavi_heads_bn_finalize": 1,
     "selavi_heads_bn_eval_affine": 1, "selavi_heads_act": 1, "selavi_heads_bn_bwd_reduce": 1,
     "selavi_heads_bn_bwd_apply": 1, "selavi_heads_sum_masked": 1, "selavi_heads_colsum": 1, "selavi_ce_loss": 2,
     "selavi_debug_umma_probe": 1, "selavi_mel_logfbank": 1, "selavi_split_bf16": 1, "selavi_p2p_allreduce_f64": 1, "selavi_conv_wgrad_bf16": 3,

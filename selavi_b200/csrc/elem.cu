@@ -379,6 +379,23 @@ __global__ void sgd_kernel(const SgdEntry* __restrict__ table, int n_tensors, fl
     }
 }
 
+constexpr int SGD_CHUNK = 48;
+struct SgdChunk {
+    SgdEntry e[SGD_CHUNK];
+};
+__global__ void sgd_chunk_kernel(const SgdChunk c, int n_tensors, float lr, float mu, float wd, int first) {
+    const int t = blockIdx.y;
+    if (t >= n_tensors) return;
+    const SgdEntry e = c.e[t];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e.n; i += (long long)gridDim.x * blockDim.x) {
+        const float p = e.p[i];
+        const float d = fmaf(wd, p, e.g[i]);
+        const float b = first ? d : fmaf(mu, e.m[i], d);
+        e.m[i] = b;
+        e.p[i] = p - lr * b;
+    }
+}
+
 }  // namespace
 
 #define LAUNCH_CHECK(what) SV_CUDA_CHECK(cudaGetLastError(), what)
@@ -542,5 +559,23 @@ extern "C" int selavi_sgd_step(const void* table, int n_tensors, float lr, float
     dim3 grid(64, n_tensors < 512 ? n_tensors : 512);
     sgd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const SgdEntry*)table, n_tensors, lr, momentum, weight_decay, first_step);
     LAUNCH_CHECK("sgd_step");
+    return 0;
+}
+
+extern "C" int selavi_sgd_step_host(void* const* params, void* const* grads, void* const* bufs, const long long* sizes,
+                                    int n_tensors, float lr, float momentum, float weight_decay, int first_step, void* stream) {
+    if (!params || !grads || !bufs || !sizes || n_tensors <= 0) return selavi_fail(-1, "sgd_step_host: bad arguments");
+    for (int t0 = 0; t0 < n_tensors; t0 += SGD_CHUNK) {
+        SgdChunk c;
+        const int n = n_tensors - t0 < SGD_CHUNK ? n_tensors - t0 : SGD_CHUNK;
+        for (int i = 0; i < n; ++i) {
+            c.e[i].p = reinterpret_cast<float*>(params[t0 + i]);
+            c.e[i].g = reinterpret_cast<const float*>(grads[t0 + i]);
+            c.e[i].m = reinterpret_cast<float*>(bufs[t0 + i]);
+            c.e[i].n = sizes[t0 + i];
+        }
+        sgd_chunk_kernel<<<dim3(64, n), 256, 0, (cudaStream_t)stream>>>(c, n, lr, momentum, weight_decay, first_step);
+        LAUNCH_CHECK("sgd_step_host");
+    }
     return 0;
 }

@@ -192,12 +192,12 @@ __global__ void heads_colsum_kernel(const float* __restrict__ x, float* __restri
 }
 
 // One block per (h, b): loss[h,b] = logsumexp(logits) - logits[label]; dlogits = (softmax - onehot) * gscale
-__global__ void ce_kernel(const void* const* logit_tbl, const long long* __restrict__ labels, long long lab_sb,
-                          long long lab_sh, int B, int K, float gscale, float* __restrict__ loss,
-                          float* __restrict__ dlogits) {
+__global__ void ce_kernel(const void* const* logit_tbl, const float* __restrict__ logits_base, long long head_stride,
+                          const long long* __restrict__ labels, long long lab_sb, long long lab_sh, int B, int K, float gscale,
+                          float* __restrict__ loss, float* __restrict__ dlogits) {
     __shared__ float red[32];
     const int h = blockIdx.y, b = blockIdx.x;
-    const float* x = reinterpret_cast<const float*>(logit_tbl[h]) + (size_t)b * K;
+    const float* x = (logit_tbl ? reinterpret_cast<const float*>(logit_tbl[h]) : logits_base + (size_t)h * head_stride) + (size_t)b * K;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     float mx = -INFINITY;
     for (int k = tid; k < K; k += blockDim.x) mx = fmaxf(mx, x[k]);
@@ -334,11 +334,11 @@ extern "C" int selavi_heads_colsum(const float* x, float* out, int H, int M, int
     return 0;
 }
 
-extern "C" int selavi_ce_loss(const void* const* logit_tbl, const long long* labels, long long lab_stride_b,
-                              long long lab_stride_h, int H, int B, int K, float grad_scale, float* loss_rows,
-                              float* loss_mean, float* dlogits, void* stream) {
-    if (!logit_tbl || !labels || !loss_rows || !loss_mean || H <= 0 || B <= 0 || K <= 0) return selavi_fail(-1, "ce_loss: bad arguments");
-    ce_kernel<<<dim3(B, H), 128, 0, (cudaStream_t)stream>>>(logit_tbl, labels, lab_stride_b, lab_stride_h, B, K, grad_scale,
+extern "C" int selavi_ce_loss(const void* const* logit_tbl, const float* logits_base, long long head_stride,
+                              const long long* labels, long long lab_stride_b, long long lab_stride_h, int H, int B, int K,
+                              float grad_scale, float* loss_rows, float* loss_mean, float* dlogits, void* stream) {
+    if ((!logit_tbl && !logits_base) || !labels || !loss_rows || !loss_mean || H <= 0 || B <= 0 || K <= 0) return selavi_fail(-1, "ce_loss: bad arguments");
+    ce_kernel<<<dim3(B, H), 128, 0, (cudaStream_t)stream>>>(logit_tbl, logits_base, head_stride, labels, lab_stride_b, lab_stride_h, B, K, grad_scale,
                                                            loss_rows, dlogits);
     LAUNCH_CHECK("ce_loss");
     mean_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(loss_rows, H * B, loss_mean);

@@ -603,7 +603,11 @@ class _CEFn(torch.autograd.Function):
         B, K = logits[0].shape
         dev = logits[0].device
         logits = [l.contiguous() for l in logits]
-        tbl = torch.tensor([l.data_ptr() for l in logits], dtype=torch.int64, device=dev)
+        # the heads of a modality are slices of ONE [H,B,K] buffer (heads_forward): address them by stride, which needs
+        # no device pointer table (building one is a synchronising host-to-device copy in the middle of the step)
+        base, stride, tbl = logits[0], B * K, None
+        if any(l.data_ptr() != base.data_ptr() + h * stride * 4 for h, l in enumerate(logits)):
+            tbl = _ptr_table(logits)
         targets = targets.to(torch.int64)
         if H == 1 and targets.dim() == 1:
             sb, sh = targets.stride(0), 0
@@ -612,7 +616,7 @@ class _CEFn(torch.autograd.Function):
         rows = torch.empty((H, B), dtype=torch.float32, device=dev)
         mean = torch.empty(1, dtype=torch.float32, device=dev)
         dl = torch.empty((H, B, K), dtype=torch.float32, device=dev)
-        _lib.check(lib.selavi_ce_loss(_lib.ptr(tbl), _lib.ptr(targets), sb, sh, H, B, K, 1.0 / (H * B), _lib.ptr(rows),
+        _lib.check(lib.selavi_ce_loss(_lib.ptr(tbl), _lib.ptr(base), stride, _lib.ptr(targets), sb, sh, H, B, K, 1.0 / (H * B), _lib.ptr(rows),
                                       _lib.ptr(mean), _lib.ptr(dl), _stream()), "selavi_ce_loss")
         ctx.dl = dl
         ctx.keep = (logits, tbl, targets)

@@ -12,6 +12,24 @@ import torch
 from . import _lib
 
 
+class _Guard:
+    """cheap device guard: only switches (and restores) the current device when the tensor lives elsewhere"""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, dev):
+        self.idx, self.prev = dev.index, None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.idx is not None and cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *a):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
 # bench.py sets PROFILE to a list: every conv launch is then bracketed by CUDA events on the launching stream
 PROFILE = None
 
@@ -107,7 +125,7 @@ def pack_weights(w, geom, mode, out=None):
         out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
     elif out.numel() != nbytes:
         raise ValueError("packed weight buffer has the wrong size")
-    with torch.cuda.device(w.device):
+    with _Guard(w.device):
         _lib.check(lib.selavi_conv_pack_weights(_lib.ptr(w), mode, geom.co, geom.ci, geom.taps, cs, _lib.ptr(out),
                                                 _lib.stream_ptr()), "selavi_conv_pack_weights")
     return out
@@ -128,7 +146,7 @@ def conv_forward(x, wpack, geom, out=None, scale=None, shift=None, relu=False, s
     if out is None:
         out = torch.empty(geom.out_shape(), dtype=torch.float32, device=x.device)
     _chk(out, geom.out_shape(), "out")
-    with torch.cuda.device(x.device), _Prof("conv_fwd", geom):
+    with _Guard(x.device), _Prof("conv_fwd", geom):
         _lib.check(_lib.lib().selavi_conv_gemm(_lib.ptr(x), _lib.ptr(out), _lib.ptr(wpack), geom.arr(0), _lib.ptr(scale),
                                                _lib.ptr(shift), 1 if relu else 0, _lib.ptr(stats), 0, passes,
                                                _lib.stream_ptr()), "selavi_conv_gemm(fwd)")
@@ -141,7 +159,7 @@ def conv_dgrad(dz, wpack_t, geom, out=None, accumulate=False, passes=3):
         out = torch.empty(geom.in_shape(), dtype=torch.float32, device=dz.device)
         accumulate = False
     _chk(out, geom.in_shape(), "dx")
-    with torch.cuda.device(dz.device), _Prof("conv_dgrad", geom):
+    with _Guard(dz.device), _Prof("conv_dgrad", geom):
         _lib.check(_lib.lib().selavi_conv_gemm(_lib.ptr(dz), _lib.ptr(out), _lib.ptr(wpack_t), geom.arr(1), None, None, 0,
                                                None, 1 if accumulate else 0, passes, _lib.stream_ptr()),
                    "selavi_conv_gemm(dgrad)")
@@ -164,7 +182,7 @@ def conv_wgrad(x, dz, geom, dw, scale=None, shift=None, relu=False, accumulate=F
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         _wgrad_ws[key] = ws
-    with torch.cuda.device(x.device), _Prof("conv_wgrad", geom):
+    with _Guard(x.device), _Prof("conv_wgrad", geom):
         _lib.check(lib.selavi_conv_wgrad(_lib.ptr(x), _lib.ptr(dz), _lib.ptr(dw), geom.arr(0), geom.ci, _lib.ptr(scale),
                                          _lib.ptr(shift), 1 if relu else 0, _lib.ptr(ws), 1 if accumulate else 0, passes,
                                          _lib.stream_ptr()), "selavi_conv_wgrad")
@@ -178,7 +196,7 @@ def split_bf16(x, scale=None, shift=None, relu=False):
         raise ValueError("split_bf16 needs a contiguous fp32 CUDA tensor")
     hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    with torch.cuda.device(x.device):
+    with _Guard(x.device):
         _lib.check(_lib.lib().selavi_split_bf16(_lib.ptr(x), _lib.ptr(scale), _lib.ptr(shift), 1 if relu else 0, _lib.ptr(hi),
                                                 _lib.ptr(lo), x.numel() // x.shape[-1], x.shape[-1], _lib.stream_ptr()),
                    "selavi_split_bf16")
@@ -196,7 +214,7 @@ def pack_weights_dgrad_bf16(w, geom, out=None):
         out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
     elif out.numel() != nbytes:
         raise ValueError("packed weight buffer has the wrong size")
-    with torch.cuda.device(w.device):
+    with _Guard(w.device):
         _lib.check(lib.selavi_dgrad_pack_weights(_lib.ptr(w), geom.co, geom.ci, geom.taps, geom.cos, _lib.ptr(out),
                                                  _lib.stream_ptr()), "selavi_dgrad_pack_weights")
     return out
@@ -214,7 +232,7 @@ def conv_dgrad_bf16(z_hi, z_lo, wpack_bf16, geom, out=None, accumulate=False, pa
         out = torch.empty(geom.in_shape(), dtype=torch.float32, device=z_hi.device)
         accumulate = False
     _chk(out, geom.in_shape(), "dx")
-    with torch.cuda.device(z_hi.device), _Prof("conv_dgrad", geom):
+    with _Guard(z_hi.device), _Prof("conv_dgrad", geom):
         _lib.check(_lib.lib().selavi_conv_dgrad_bf16(_lib.ptr(z_hi), _lib.ptr(z_lo), _lib.ptr(out), _lib.ptr(wpack_bf16),
                                                      geom.arr(1), 1 if accumulate else 0, passes, _lib.stream_ptr()),
                    "selavi_conv_dgrad_bf16")
@@ -234,7 +252,7 @@ def conv_wgrad_bf16(x, z_hi, z_lo, geom, dw, scale=None, shift=None, relu=False,
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         _wgrad_ws[key] = ws
-    with torch.cuda.device(x.device), _Prof("conv_wgrad", geom):
+    with _Guard(x.device), _Prof("conv_wgrad", geom):
         _lib.check(lib.selavi_conv_wgrad_bf16(_lib.ptr(x), _lib.ptr(z_hi), _lib.ptr(z_lo), _lib.ptr(dw), geom.arr(0), geom.ci,
                                               _lib.ptr(scale), _lib.ptr(shift), 1 if relu else 0, _lib.ptr(ws),
                                               1 if accumulate else 0, passes, _lib.stream_ptr()), "selavi_conv_wgrad_bf16")

@@ -4,6 +4,8 @@ Same update rule and constructor as `torch.optim.SGD(params, lr, momentum, weigh
 main.py:132-137 (dampening 0, no nesterov): d = g + wd*p; buf = d on the first step else mu*buf + d; p -= lr*buf.
 `state_dict()` uses torch's layout (`momentum_buffer` per parameter), so checkpoints are interchangeable.
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -35,18 +37,16 @@ class SGD(torch.optim.Optimizer):
                     first = True
                 if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()):
                     raise ValueError("selavi_b200.optim.SGD needs contiguous fp32 CUDA parameters and gradients")
-            key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["momentum_buffer"].data_ptr()) for p in ps)
-            tbl = self._tables.get(gi)
-            if tbl is None or tbl[0] != key:
-                rows = []
-                for p in ps:
-                    rows += [p.data_ptr(), p.grad.data_ptr(), self.state[p]["momentum_buffer"].data_ptr(), p.numel()]
-                tbl = (key, torch.tensor(rows, dtype=torch.int64, device=ps[0].device))
-                self._tables[gi] = tbl
+            n = len(ps)
+            arr = ctypes.c_void_p * n
+            params = arr(*[p.data_ptr() for p in ps])
+            grads = arr(*[p.grad.data_ptr() for p in ps])
+            bufs = arr(*[self.state[p]["momentum_buffer"].data_ptr() for p in ps])
+            sizes = (ctypes.c_longlong * n)(*[p.numel() for p in ps])
             with torch.cuda.device(ps[0].device):
-                _lib.check(lib.selavi_sgd_step(_lib.ptr(tbl[1]), len(ps), float(group["lr"]), float(group["momentum"]),
-                                               float(group["weight_decay"]), 1 if first else 0, _lib.stream_ptr()),
-                           "selavi_sgd_step")
+                _lib.check(lib.selavi_sgd_step_host(params, grads, bufs, sizes, n, float(group["lr"]), float(group["momentum"]),
+                                                    float(group["weight_decay"]), 1 if first else 0, _lib.stream_ptr()),
+                           "selavi_sgd_step_host")
             # the kernel wrote the parameters behind autograd's back: bump their version counters so that
             # version-keyed caches (the packed tensor-core weights in engine.py) see the update
             torch.autograd.graph.increment_version(ps)
