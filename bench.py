@@ -216,7 +216,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     agg = {}
-    for kind, flops, e0, e1 in prof:
+    if os.environ.get("SELAVI_BENCH_DETAIL") and rank == 0:
+        for kind, flops, e0, e1, tag in prof:
+            ms = e0.elapsed_time(e1)
+            print(f"DETAIL {kind:11s} ci,co,T,H,W,k,s={tag} {ms:8.3f} ms {flops / ms / 1e9:7.1f} TF/s", file=sys.stderr)
+    for kind, flops, e0, e1, _tag in prof:
         a = agg.setdefault(kind, [0.0, 0.0, 0])
         a[0] += flops
         a[1] += e0.elapsed_time(e1)

@@ -39,6 +39,7 @@ class _Prof:
         self.on = PROFILE is not None
         if self.on:
             self.kind, self.flops = kind, 2.0 * geom.m_out * geom.co * geom.ci * geom.taps
+            self.tag = (geom.ci, geom.co, geom.ti, geom.hi, geom.wi, geom.kt, geom.kh, geom.kw, geom.st, geom.sh)
             self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def __enter__(self):
@@ -48,7 +49,7 @@ class _Prof:
     def __exit__(self, *a):
         if self.on:
             self.e1.record()
-            PROFILE.append((self.kind, self.flops, self.e0, self.e1))
+            PROFILE.append((self.kind, self.flops, self.e0, self.e1, self.tag))
 
 
 def padc(c):
