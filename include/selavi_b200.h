@@ -85,14 +85,15 @@ int selavi_conv_wgrad(const float* src, const float* dz, float* dW, const int* g
                       int passes, void* stream);
 /* bf16x3 backward on pre-split gradients: z_hi/z_lo = bf16 hi/lo planes [M, cd] of the gradient wrt the conv output
  * (from selavi_bn_bwd_apply or selavi_split_bf16).  wgrad_bf16: same contract as selavi_conv_wgrad (passes 3 or 1).
- * dgrad_bf16: geom in mode 1; wpack from selavi_dgrad_pack_weights (W[co][ci][taps], cs = channel stride of dz). */
+ * dgrad_bf16: geom in mode 1; wpack from selavi_dgrad_pack_weights(W[co][ci][taps], same geom).  Strided convs are
+ * processed per stride-parity class of the input pixels, each with its own tap subset (no zero-filled MMA work). */
 int selavi_split_bf16(const float* x, const float* scale, const float* shift, int relu, void* hi, void* lo, long long M,
                       int cs, void* stream);
 int selavi_conv_wgrad_bf16(const float* src, const void* z_hi, const void* z_lo, float* dW, const int* geom, int ci_real,
                            const float* pro_scale, const float* pro_shift, int pro_relu, void* workspace, int accumulate,
                            int passes, void* stream);
-size_t selavi_dgrad_wpack_bytes(int ci, int k_total);
-int selavi_dgrad_pack_weights(const float* W, int co, int ci, int taps, int cs, void* wpack, void* stream);
+size_t selavi_dgrad_wpack_bytes(const int* geom);
+int selavi_dgrad_pack_weights(const float* W, const int* geom, int co, void* wpack, void* stream);
 int selavi_conv_dgrad_bf16(const void* z_hi, const void* z_lo, float* dx, const void* wpack, const int* geom,
                            int accumulate, int passes, void* stream);
 

@@ -51,8 +51,8 @@ SIGNATURES = {
     "selavi_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "selavi_conv_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                        c_void_p, c_int, c_int, c_void_p]),
-    "selavi_dgrad_wpack_bytes": (c_size_t, [c_int, c_int]),
-    "selavi_dgrad_pack_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "selavi_dgrad_wpack_bytes": (c_size_t, [c_void_p]),
+    "selavi_dgrad_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "selavi_conv_dgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "selavi_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "selavi_maxpool3x3s2_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

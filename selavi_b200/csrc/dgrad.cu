@@ -29,7 +29,24 @@ constexpr int DG_A_BYTES = DG_BM * 128;     // 128 pixels x 64 bf16 channels
 constexpr int DG_MAX_TAPS = 64;
 constexpr int DG_MAX_STAGES = 6;
 
+// Stride-2 convolutions: an input pixel only receives contributions from the taps whose parity matches
+// (dst + pad - k) % stride == 0, i.e. 1/stride of the taps per strided dimension.  Pixels are therefore processed
+// in parity classes (up to st*sh*sw of them): a tile holds 128 pixels of ONE class and its K loop runs over that
+// class's taps only (no zero-filled MMA work: 2.25 instead of 9 taps on average for a 3x3 stride-2 conv).
+constexpr int DG_MAX_CLASSES = 8;
+struct DgClass {
+    int o[3];        // first dst coordinate of the class per dimension (t, h, w)
+    int n[3];        // number of dst coordinates of the class per dimension
+    int pixels;      // nb * n[0] * n[1] * n[2]
+    int tile_begin;  // first tile (in units of m-tiles) of the class
+    int ntaps, kstages;
+    long long woff;  // byte offset of the class's packed weights
+    unsigned char taps[DG_MAX_TAPS];
+};
+
 struct DgradParams {
+    int nclasses;
+    DgClass cls[DG_MAX_CLASSES];
     const __nv_bfloat16* z_hi;   // [pixels_out][cs] gradient wrt the conv output, split
     const __nv_bfloat16* z_lo;
     float* dst;                  // [M = pixels_in][cd]
@@ -37,7 +54,7 @@ struct DgradParams {
     int nb, ts, hs, ws, cs;      // gathered tensor (dz) geometry: forward OUTPUT dims
     int td, hd, wd, cd;          // dx geometry: forward INPUT dims
     int kt, kh, kw, st, sh, sw, pt, ph, pw;
-    int M, m_tiles, kstages, bnt, ntiles, stages, accumulate, passes;
+    int M, m_tiles, bnt, ntiles, stages, accumulate, passes;
     uint32_t tmem_cols;
 };
 
@@ -101,7 +118,12 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_bf16_kernel(const DgradPa
         int stage = 0, prev_stage = -1;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m0 = (tile / p.ntiles) * DG_BM;
+            const int m_tile = tile / p.ntiles;
+            int ci = 0;
+            while (ci + 1 < p.nclasses && m_tile >= p.cls[ci + 1].tile_begin) ++ci;
+            const DgClass& cl = p.cls[ci];
+            const int m0 = (m_tile - cl.tile_begin) * DG_BM;   // first row of the tile inside its class
+            const int kstages = cl.kstages;
             int pb[4];
             uint32_t vm[4];
 #pragma unroll
@@ -109,13 +131,14 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_bf16_kernel(const DgradPa
                 const int m = m0 + r0 + 32 * j;
                 pb[j] = 0;
                 vm[j] = 0;
-                if (m < p.M) {
-                    const int w_ = m % p.wd;
-                    const int t1 = m / p.wd;
-                    const int h_ = t1 % p.hd;
-                    const int t2 = t1 / p.hd;
-                    const int t_ = t2 % p.td;
-                    const int n_ = t2 / p.td;
+                if (m < cl.pixels) {
+                    const int iw = m % cl.n[2];
+                    const int t1 = m / cl.n[2];
+                    const int ih = t1 % cl.n[1];
+                    const int t2 = t1 / cl.n[1];
+                    const int it_ = t2 % cl.n[0];
+                    const int n_ = t2 / cl.n[0];
+                    const int w_ = cl.o[2] + iw * p.sw, h_ = cl.o[1] + ih * p.sh, t_ = cl.o[0] + it_ * p.st;
                     const int at = t_ + p.pt, ah = h_ + p.ph, aw = w_ + p.pw;
                     uint32_t mt = 0, mh = 0, mw = 0;
                     for (int k = 0; k < p.kt; ++k) {
@@ -141,20 +164,21 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_bf16_kernel(const DgradPa
                     vm[j] = mt | (mh << 8) | (mw << 16) | 0x80000000u;
                 }
             }
-            int tap = 0, c8 = c;  // flattened K chunk q = 8*ks + c -> (tap, c8)
+            int tap = 0, c8 = c;  // flattened K chunk q = 8*ks + c -> (index in the class's tap list, c8)
             while (c8 >= C8) {
                 c8 -= C8;
                 ++tap;
             }
-            for (int ks = 0; ks < p.kstages; ++ks) {
+            for (int ks = 0; ks < kstages; ++ks) {
                 sv::mbar_wait(&empty_bar[stage], phase ^ 1);
                 const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint32_t a_lo = a_hi + DG_A_BYTES;
                 int pk = 0, off = 0;
-                const bool kvalid = tap < taps;
+                const bool kvalid = tap < cl.ntaps;
                 if (kvalid) {
-                    pk = tap_dt[tap];
-                    off = tap_off[tap];
+                    const int tp = cl.taps[tap];
+                    pk = tap_dt[tp];
+                    off = tap_off[tp];
                 }
                 const int s_t = pk & 255, s_h = 8 + ((pk >> 8) & 255), s_w = 16 + ((pk >> 16) & 255);
 #pragma unroll
@@ -176,7 +200,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_bf16_kernel(const DgradPa
                 }
                 prev_stage = stage;
                 c8 += 8;
-                while (c8 >= C8 && tap < taps) {
+                while (c8 >= C8 && tap < cl.ntaps) {
                     c8 -= C8;
                     ++tap;
                 }
@@ -198,10 +222,23 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_bf16_kernel(const DgradPa
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const int m_tile = tile / p.ntiles, ntile = tile % p.ntiles;
-            const int m = m_tile * DG_BM + quad * 32 + lane;
-            const bool row_ok = m < p.M;
+            int ci = 0;
+            while (ci + 1 < p.nclasses && m_tile >= p.cls[ci + 1].tile_begin) ++ci;
+            const DgClass& cl = p.cls[ci];
+            const int mc = (m_tile - cl.tile_begin) * DG_BM + quad * 32 + lane;   // row inside the class
+            const bool row_ok = mc < cl.pixels;
+            int m = 0;
+            if (row_ok) {
+                const int iw = mc % cl.n[2];
+                const int t1 = mc / cl.n[2];
+                const int ih = t1 % cl.n[1];
+                const int t2 = t1 / cl.n[1];
+                const int it_ = t2 % cl.n[0];
+                const int n_ = t2 / cl.n[0];
+                m = ((n_ * p.td + cl.o[0] + it_ * p.st) * p.hd + cl.o[1] + ih * p.sh) * p.wd + cl.o[2] + iw * p.sw;
+            }
             const int n_base = ntile * p.bnt;
-            float* out_row = p.dst + (size_t)(row_ok ? m : 0) * p.cd;
+            float* out_row = p.dst + (size_t)m * p.cd;
             sv::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
             sv::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * (p.tmem_cols >> 1);
@@ -240,10 +277,14 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_bf16_kernel(const DgradPa
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
+                const int m_tile = tile / p.ntiles;
+                int ci = 0;
+                while (ci + 1 < p.nclasses && m_tile >= p.cls[ci + 1].tile_begin) ++ci;
+                const int kstages = p.cls[ci].kstages;
                 sv::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
                 sv::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * (p.tmem_cols >> 1);
-                for (int ks = 0; ks < p.kstages; ++ks) {
+                for (int ks = 0; ks < kstages; ++ks) {
                     sv::mbar_wait(&full_bar[stage], phase);
                     sv::tc_fence_after();
                     const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
@@ -279,9 +320,12 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_bf16_kernel(const DgradPa
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int ntile = tile % p.ntiles;
-                const unsigned char* wsrc = p.wpack + (size_t)ntile * p.kstages * 2 * b_tile_bytes;
-                for (int ks = 0; ks < p.kstages; ++ks) {
+                const int ntile = tile % p.ntiles, m_tile = tile / p.ntiles;
+                int ci = 0;
+                while (ci + 1 < p.nclasses && m_tile >= p.cls[ci + 1].tile_begin) ++ci;
+                const int kstages = p.cls[ci].kstages;
+                const unsigned char* wsrc = p.wpack + p.cls[ci].woff + (size_t)ntile * kstages * 2 * b_tile_bytes;
+                for (int ks = 0; ks < kstages; ++ks) {
                     sv::mbar_wait(&empty_bar[stage], phase ^ 1);
                     sv::mbar_arrive_expect_tx(&full_bar[stage], bytes);
                     sv::bulk_g2s(smem + (size_t)stage * stage_bytes + 2 * DG_A_BYTES, wsrc + (size_t)ks * 2 * b_tile_bytes,
@@ -303,8 +347,12 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_bf16_kernel(const DgradPa
 
 // W [co][ci][taps] -> B operand of the data gradient in bf16 hi/lo: n = ci, k = tap*cs + co (cs = padded co),
 // tiles [ntile][kstage of 64 k][hi|lo][bnt rows][128 B], 128B-swizzled.
-__global__ void dgrad_pack_weights_bf16_kernel(const float* __restrict__ W, int co, int ci, int taps, int cs, int bnt,
-                                               int ntiles, int kstages, __nv_bfloat16* __restrict__ out) {
+struct DgTapList {
+    int ntaps;
+    unsigned char taps[DG_MAX_TAPS];
+};
+__global__ void dgrad_pack_weights_bf16_kernel(const float* __restrict__ W, int co, int ci, int taps_total, const DgTapList tl,
+                                               int cs, int bnt, int ntiles, int kstages, __nv_bfloat16* __restrict__ out) {
     const size_t total = (size_t)ntiles * kstages * bnt * 64;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int e = (int)(idx & 7);
@@ -314,10 +362,10 @@ __global__ void dgrad_pack_weights_bf16_kernel(const float* __restrict__ W, int 
         const int ks = (int)(blk % kstages);
         const int nt = (int)(blk / kstages);
         const int k = ks * 64 + c * 8 + e;
-        const int tap = k / cs, kc = k % cs;
+        const int tj = k / cs, kc = k % cs;
         const int nn = nt * bnt + n;
         float val = 0.f;
-        if (tap < taps && nn < ci && kc < co) val = W[((size_t)kc * ci + nn) * taps + tap];
+        if (tj < tl.ntaps && nn < ci && kc < co) val = W[((size_t)kc * ci + nn) * taps_total + tl.taps[tj]];
         const __nv_bfloat16 hi = __float2bfloat16_rn(val);
         const __nv_bfloat16 lo = __float2bfloat16_rn(val - __bfloat162float(hi));
         __nv_bfloat16* base = out + blk * (size_t)(2 * bnt * 64);
@@ -335,24 +383,77 @@ void dg_tiles(int n_out, int* bnt, int* ntiles) {
     *ntiles = nt;
 }
 
-}  // namespace
+struct DgPlan {
+    int nclasses, bnt, ntiles, m_tiles;
+    DgClass cls[DG_MAX_CLASSES];
+    size_t wbytes;
+};
 
-extern "C" size_t selavi_dgrad_wpack_bytes(int ci, int k_total) {
-    int bnt, nt;
-    dg_tiles(ci, &bnt, &nt);
-    return (size_t)nt * ((k_total + 63) / 64) * 2 * bnt * 128;
+// geom in dgrad mode: [1, nb, ts,hs,ws,cs (dz: forward OUTPUT dims), td,hd,wd,cd (dx: forward INPUT dims), kt,kh,kw, st,sh,sw, pt,ph,pw, ci]
+int dg_plan(const int* g, DgPlan* pl) {
+    const int nb = g[1], D[3] = {g[6], g[7], g[8]}, K[3] = {g[10], g[11], g[12]}, S[3] = {g[13], g[14], g[15]}, P[3] = {g[16], g[17], g[18]};
+    const int cs = g[5], n_out = g[19];
+    if (K[0] * K[1] * K[2] > DG_MAX_TAPS) return -1;
+    dg_tiles(n_out, &pl->bnt, &pl->ntiles);
+    pl->nclasses = 0;
+    int tile = 0;
+    size_t woff = 0;
+    for (int rt = 0; rt < S[0]; ++rt)
+        for (int rh = 0; rh < S[1]; ++rh)
+            for (int rw = 0; rw < S[2]; ++rw) {
+                const int r[3] = {rt, rh, rw};
+                DgClass c;
+                c.pixels = nb;
+                for (int d = 0; d < 3; ++d) {
+                    c.o[d] = ((r[d] - P[d]) % S[d] + S[d]) % S[d];      // dst = o + S*i  <=>  (dst + pad) % S == r
+                    c.n[d] = c.o[d] < D[d] ? (D[d] - c.o[d] + S[d] - 1) / S[d] : 0;
+                    c.pixels *= c.n[d];
+                }
+                if (c.pixels == 0) continue;
+                c.ntaps = 0;
+                for (int kt = 0; kt < K[0]; ++kt)
+                    for (int kh = 0; kh < K[1]; ++kh)
+                        for (int kw = 0; kw < K[2]; ++kw)
+                            if (kt % S[0] == rt && kh % S[1] == rh && kw % S[2] == rw)
+                                c.taps[c.ntaps++] = (unsigned char)((kt * K[1] + kh) * K[2] + kw);
+                // a class without taps still has to be written (zeros): give it one K stage of zero weights
+                c.kstages = c.ntaps > 0 ? (c.ntaps * (cs >> 3) + 7) / 8 : 1;
+                c.tile_begin = tile;
+                c.woff = (long long)woff;
+                tile += (c.pixels + DG_BM - 1) / DG_BM;
+                woff += (size_t)pl->ntiles * c.kstages * 2 * pl->bnt * 128;
+                pl->cls[pl->nclasses++] = c;
+            }
+    pl->m_tiles = tile;
+    pl->wbytes = woff;
+    return 0;
 }
 
-extern "C" int selavi_dgrad_pack_weights(const float* W, int co, int ci, int taps, int cs, void* wpack, void* stream) {
-    if (!W || !wpack || co <= 0 || ci <= 0 || taps <= 0 || (cs & 7)) return selavi_fail(-1, "dgrad_pack_weights: bad arguments");
-    int bnt, nt;
-    dg_tiles(ci, &bnt, &nt);
-    const int kstages = (taps * cs + 63) / 64;
-    const size_t total = (size_t)nt * kstages * bnt * 64;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    dgrad_pack_weights_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, co, ci, taps, cs, bnt, nt, kstages,
-                                                                             reinterpret_cast<__nv_bfloat16*>(wpack));
+}  // namespace
+
+extern "C" size_t selavi_dgrad_wpack_bytes(const int* geom) {
+    DgPlan pl;
+    if (!geom || dg_plan(geom, &pl) != 0) return 0;
+    return pl.wbytes;
+}
+
+extern "C" int selavi_dgrad_pack_weights(const float* W, const int* geom, int co, void* wpack, void* stream) {
+    if (!W || !wpack || !geom || co <= 0) return selavi_fail(-1, "dgrad_pack_weights: bad arguments");
+    DgPlan pl;
+    if (dg_plan(geom, &pl) != 0) return selavi_fail(-1, "dgrad_pack_weights: kernel too large");
+    const int ci = geom[19], cs = geom[5], taps = geom[10] * geom[11] * geom[12];
+    if (cs & 7) return selavi_fail(-1, "dgrad_pack_weights: channel stride must be a multiple of 8");
+    for (int c = 0; c < pl.nclasses; ++c) {
+        DgTapList tl;
+        tl.ntaps = pl.cls[c].ntaps;
+        for (int j = 0; j < tl.ntaps; ++j) tl.taps[j] = pl.cls[c].taps[j];
+        const size_t total = (size_t)pl.ntiles * pl.cls[c].kstages * pl.bnt * 64;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        dgrad_pack_weights_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+            W, co, ci, taps, tl, cs, pl.bnt, pl.ntiles, pl.cls[c].kstages,
+            reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(wpack) + pl.cls[c].woff));
+    }
     SV_CUDA_CHECK(cudaGetLastError(), "dgrad_pack_weights: launch");
     return 0;
 }
@@ -372,7 +473,6 @@ extern "C" int selavi_conv_dgrad_bf16(const void* z_hi, const void* z_lo, float*
     p.kt = geom[10]; p.kh = geom[11]; p.kw = geom[12];
     p.st = geom[13]; p.sh = geom[14]; p.sw = geom[15];
     p.pt = geom[16]; p.ph = geom[17]; p.pw = geom[18];
-    const int n_out = geom[19];
     if ((p.cs & 7) || (p.cd & 3)) return selavi_fail(-1, "conv_dgrad_bf16: bad channel strides");
     if (p.kt * p.kh * p.kw > DG_MAX_TAPS || p.kt > 8 || p.kh > 8 || p.kw > 8) return selavi_fail(-1, "conv_dgrad_bf16: kernel too large");
     if ((p.st != 1 && p.st != 2) || (p.sh != 1 && p.sh != 2) || (p.sw != 1 && p.sw != 2)) return selavi_fail(-1, "conv_dgrad_bf16: stride must be 1 or 2");
@@ -380,10 +480,11 @@ extern "C" int selavi_conv_dgrad_bf16(const void* z_hi, const void* z_lo, float*
     const long long M = (long long)p.nb * p.td * p.hd * p.wd;
     if (M <= 0 || M > 0x7fffffffLL || (long long)p.nb * p.ts * p.hs * p.ws > 0x7fffffffLL) return selavi_fail(-1, "conv_dgrad_bf16: bad pixel count");
     p.M = (int)M;
-    dg_tiles(n_out, &p.bnt, &p.ntiles);
+    DgPlan pl;
+    if (dg_plan(geom, &pl) != 0) return selavi_fail(-1, "conv_dgrad_bf16: kernel too large");
+    p.bnt = pl.bnt; p.ntiles = pl.ntiles; p.m_tiles = pl.m_tiles; p.nclasses = pl.nclasses;
+    for (int c = 0; c < pl.nclasses; ++c) p.cls[c] = pl.cls[c];
     if (p.ntiles * p.bnt < p.cd) return selavi_fail(-1, "conv_dgrad_bf16: cd exceeds the tiled channel range");
-    p.kstages = (p.kt * p.kh * p.kw * (p.cs >> 3) + 7) / 8;
-    p.m_tiles = (p.M + DG_BM - 1) / DG_BM;
     p.accumulate = accumulate;
     p.passes = passes;
     uint32_t cols = 32;

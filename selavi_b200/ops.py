@@ -210,14 +210,14 @@ def pack_weights_dgrad_bf16(w, geom, out=None):
     if not (w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()):
         raise ValueError("weight must be a contiguous fp32 CUDA tensor")
     lib = _lib.lib()
-    nbytes = lib.selavi_dgrad_wpack_bytes(geom.ci, geom.taps * geom.cos)
+    nbytes = lib.selavi_dgrad_wpack_bytes(geom.arr(1))
     if out is None:
         out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
     elif out.numel() != nbytes:
         raise ValueError("packed weight buffer has the wrong size")
     with _Guard(w.device):
-        _lib.check(lib.selavi_dgrad_pack_weights(_lib.ptr(w), geom.co, geom.ci, geom.taps, geom.cos, _lib.ptr(out),
-                                                 _lib.stream_ptr()), "selavi_dgrad_pack_weights")
+        _lib.check(lib.selavi_dgrad_pack_weights(_lib.ptr(w), geom.arr(1), geom.co, _lib.ptr(out), _lib.stream_ptr()),
+                   "selavi_dgrad_pack_weights")
     return out
 
 
