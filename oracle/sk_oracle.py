@@ -77,3 +77,38 @@ def synth_PS(N, K, scale=1.0, seed=0):
         return e / e.sum(1, keepdims=True)
 
     return sm(rng.standard_normal((N, K)) * scale) * sm(rng.standard_normal((N, K)) * scale)
+
+
+def match_order_oracle(emb1, emb2_in, steps=50000, restarts=2):
+    """CPU restatement of the permutation search of src/sk_utils.py:424-467 (`match_order`): random pair swaps
+    (np.random.choice stream) that reduce sum |emb1 - emb2[:, perm]|, early stop after 1000 non-improving steps,
+    best of `restarts` tries if it beats the identity.  Returns the permutation applied to the audio head rows."""
+    emb1 = np.asarray(emb1, dtype=np.float64)
+    emb2_in = np.asarray(emb2_in, dtype=np.float64)
+    K = emb1.shape[1]
+
+    def c(a, b):
+        return np.abs(a - b).sum()
+
+    fin_perm = np.arange(K)
+    last_iter = 0
+    cost = c(emb1, emb2_in)
+    best_cost = cost
+    for _ in range(restarts):
+        perm = np.arange(K)
+        emb2 = emb2_in.copy()
+        for _iter in range(steps):
+            i, j = np.random.choice(K, 2, replace=False)
+            current = c(emb1[:, i], emb2[:, i]) + c(emb1[:, j], emb2[:, j])
+            future = c(emb1[:, i], emb2[:, j]) + c(emb1[:, j], emb2[:, i])
+            if current - future > 0:
+                emb2[:, [i, j]] = emb2[:, [j, i]]
+                perm[i], perm[j] = perm[j], perm[i]
+                last_iter = _iter
+            if _iter - last_iter > 1000:
+                break
+        cost_try = c(emb1, emb2_in[:, perm])
+        if cost_try < best_cost:
+            best_cost = cost_try
+            fin_perm = perm.copy()
+    return fin_perm

@@ -201,29 +201,41 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* 
                                     const float4* __restrict__ act, int mask_mode, const float4* __restrict__ scale,
                                     const float4* __restrict__ shift, const float4* __restrict__ mean,
                                     const float4* __restrict__ invstd, const double* __restrict__ sums, double count,
-                                    long long total4, int c4n, float4* __restrict__ dz, float4* __restrict__ gres,
+                                    long long M, int c4n, float4* __restrict__ dz, float4* __restrict__ gres,
                                     int gres_accumulate, uint2* __restrict__ dz_hi, uint2* __restrict__ dz_lo) {
-    const int cs = c4n * 4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-        const int c4 = (int)(i % c4n);
+    // grid (row blocks, ceil(c4n/32)), 256 threads: lane -> channel chunk (per-channel constants live in registers),
+    // warp -> row; dz = A*g + B*z + C with A = scale, B = -scale*invstd*m2, C = -scale*m1 + scale*invstd*m2*mean
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c4 = blockIdx.y * 32 + lane;
+    if (c4 >= c4n) return;
+    const int cs = c4n * 4, c = c4 * 4;
+    const float4 sc = __ldg(scale + c4), mu = __ldg(mean + c4), is = __ldg(invstd + c4);
+    float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mask_mode == 2) sh = __ldg(shift + c4);
+    const double inv = 1.0 / count;
+    const float m1x = (float)(sums[c] * inv), m1y = (float)(sums[c + 1] * inv), m1z = (float)(sums[c + 2] * inv),
+                m1w = (float)(sums[c + 3] * inv);
+    const float m2x = (float)(sums[cs + c] * inv), m2y = (float)(sums[cs + c + 1] * inv), m2z = (float)(sums[cs + c + 2] * inv),
+                m2w = (float)(sums[cs + c + 3] * inv);
+    const float4 B = make_float4(-sc.x * is.x * m2x, -sc.y * is.y * m2y, -sc.z * is.z * m2z, -sc.w * is.w * m2w);
+    const float4 C = make_float4(-sc.x * m1x - B.x * mu.x, -sc.y * m1y - B.y * mu.y, -sc.z * m1z - B.z * mu.z,
+                                 -sc.w * m1w - B.w * mu.w);
+    const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > M) r1 = M;
+    for (long long r = r0 + warp; r < r1; r += 8) {
+        const size_t i = (size_t)r * c4n + c4;
         const float4 zz = z[i];
-        const float4 sc = __ldg(scale + c4);
         float4 a = zz;
         if (mask_mode == 1) a = act[i];
-        else if (mask_mode == 2) a = affine4(zz, sc, __ldg(shift + c4));
+        else if (mask_mode == 2) a = affine4(zz, sc, sh);
         const float4 gg = masked_g(g[i], mask_mode, a);
-        const float4 mu = __ldg(mean + c4), is = __ldg(invstd + c4);
-        const int c = c4 * 4;
-        const float inv = (float)(1.0 / count);
-        const float m1x = (float)sums[c] * inv, m1y = (float)sums[c + 1] * inv, m1z = (float)sums[c + 2] * inv,
-                    m1w = (float)sums[c + 3] * inv;
-        const float m2x = (float)sums[cs + c] * inv, m2y = (float)sums[cs + c + 1] * inv, m2z = (float)sums[cs + c + 2] * inv,
-                    m2w = (float)sums[cs + c + 3] * inv;
         float4 o;
-        o.x = sc.x * (gg.x - m1x - (zz.x - mu.x) * is.x * m2x);
-        o.y = sc.y * (gg.y - m1y - (zz.y - mu.y) * is.y * m2y);
-        o.z = sc.z * (gg.z - m1z - (zz.z - mu.z) * is.z * m2z);
-        o.w = sc.w * (gg.w - m1w - (zz.w - mu.w) * is.w * m2w);
+        o.x = fmaf(sc.x, gg.x, fmaf(B.x, zz.x, C.x));
+        o.y = fmaf(sc.y, gg.y, fmaf(B.y, zz.y, C.y));
+        o.z = fmaf(sc.z, gg.z, fmaf(B.z, zz.z, C.z));
+        o.w = fmaf(sc.w, gg.w, fmaf(B.w, zz.w, C.w));
         if (dz) dz[i] = o;
         if (dz_hi) {   // bf16 hi/lo planes for the bf16x3 data / weight gradient kernels
             const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
@@ -233,12 +245,12 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* 
             dz_lo[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
         }
         if (gres) {
-            float4 r = gg;
+            float4 rr = gg;
             if (gres_accumulate) {
                 const float4 old = gres[i];
-                r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+                rr.x += old.x; rr.y += old.y; rr.z += old.z; rr.w += old.w;
             }
-            gres[i] = r;
+            gres[i] = rr;
         }
     }
 }
@@ -491,10 +503,15 @@ extern "C" int selavi_bn_bwd_apply(const float* g, const float* z, const float* 
         return selavi_fail(-1, "bn_bwd_apply: bad arguments");
     if (mask_mode == 1 && !act) return selavi_fail(-1, "bn_bwd_apply: mask_mode 1 needs act");
     if (mask_mode == 2 && !shift) return selavi_fail(-1, "bn_bwd_apply: mask_mode 2 needs shift");
-    const long long total4 = M * (cs / 4);
-    bn_bwd_apply_kernel<<<ew_blocks(total4), EW_THREADS, 0, (cudaStream_t)stream>>>(
+    const int c4n = cs / 4;
+    long long nblk = (M + 31) / 32;
+    const long long cap = (148LL * 16) / ((c4n + 31) / 32);
+    if (nblk > cap) nblk = cap;
+    if (nblk < 1) nblk = 1;
+    dim3 grid((unsigned)nblk, (c4n + 31) / 32);
+    bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         (const float4*)g, (const float4*)z, (const float4*)act, mask_mode, (const float4*)scale, (const float4*)shift,
-        (const float4*)mean, (const float4*)invstd, sums, count, total4, cs / 4, (float4*)dz, (float4*)gres, gres_accumulate,
+        (const float4*)mean, (const float4*)invstd, sums, count, M, c4n, (float4*)dz, (float4*)gres, gres_accumulate,
         (uint2*)dz_hi, (uint2*)dz_lo);
     LAUNCH_CHECK("bn_bwd_apply");
     return 0;

@@ -97,3 +97,33 @@ def test_sweep_single_gpu_matches_oracle(cuda_device):
             torch.testing.assert_close(PS, ref, rtol=1e-12, atol=0)
             ora = optimize_L_sk(PS.cpu().numpy())
             assert np.array_equal(L[:, head].cpu().numpy(), ora["labels"])
+
+
+@pytest.mark.gpu
+def test_match_order_matches_oracle(cuda_device):
+    """match_order (K x K L1 cost matrix + host hill-climb on it) picks the same permutation as the reference's
+    column-swapping search for the same np.random stream, and permutes the Linear rows accordingly."""
+    from oracle.sk_oracle import match_order_oracle
+    from selavi_b200.sk_utils import match_order
+    rng = np.random.default_rng(3)
+    N, K = 400, 12
+    true_perm = rng.permutation(K)
+    lv = rng.standard_normal((N, K)) * 3
+    la = lv[:, true_perm] + 0.05 * rng.standard_normal((N, K))            # audio head = permuted video head + noise
+
+    def sm(x):
+        e = np.exp(x - x.max(1, keepdims=True))
+        return e / e.sum(1, keepdims=True)
+
+    np.random.seed(11)
+    ref = match_order_oracle(sm(lv), sm(la))
+    lin = torch.nn.Linear(5, K).to(cuda_device)
+    w0, b0 = lin.weight.data.clone(), lin.bias.data.clone()
+    args = types.SimpleNamespace(rank=0)
+    np.random.seed(11)
+    fin = match_order(args, torch.from_numpy(lv).float().to(cuda_device), torch.from_numpy(la).float().to(cuda_device), lin,
+                      logits=True)
+    assert np.array_equal(fin.cpu().numpy(), ref)
+    assert torch.equal(lin.weight.data, w0[fin]) and torch.equal(lin.bias.data, b0[fin])
+    # the search must actually have aligned the heads: emb2[:, perm] ~ emb1
+    assert np.abs(sm(lv) - sm(la)[:, ref]).sum() < 0.2 * np.abs(sm(lv) - sm(la)).sum()

@@ -83,6 +83,40 @@ def main():
         worst = max(worst, e)
     print(f"[rank {rank}] DDP+SyncBN vs single GPU: loss {float(l_ddp):.6f} vs {float(l_single):.6f}, worst grad rel err {worst:.2e}", flush=True)
     ok &= abs(float(l_ddp) - float(l_single)) < 1e-4 * abs(float(l_single)) and worst < 5e-3
+    # ---- 3. row-sharded dataset sweep + label assignment (get_cluster_assignments_gpu) == single-GPU result
+    from selavi_b200.sk_utils import get_cluster_assignments_gpu
+
+    class Clips(torch.utils.data.Dataset):
+        def __init__(self, n):
+            r = np.random.default_rng(5)
+            self.v = torch.from_numpy(r.standard_normal((n, 3, 4, 32, 32)).astype(np.float32) * np.linspace(0.5, 2, n, dtype=np.float32).reshape(n, 1, 1, 1, 1))
+            self.a = torch.from_numpy((r.standard_normal((n, 1, 65, 40)) * 17.89 + 1.93).astype(np.float32))
+
+        def __len__(self):
+            return len(self.v)
+
+        def __getitem__(self, i):
+            return self.v[i], self.a[i], 0, i, i
+
+    ds = Clips(96)
+    torch.manual_seed(31)
+    m1 = sv_model.load_model(use_mlp=True, headcount=2, num_classes=8, norm_feat=False).to(dev)
+    sargs = types.SimpleNamespace(world_size=1, rank=0, workers=0, ind_groups=1, headcount=2, match=False, distribution="default",
+                                  dist=None, diff_dist_every=False, diff_dist_per_head=True, gauss_sd=0.1, lamb=20.0, dump_path="")
+    import selavi_b200.sk_utils as sku
+    np.random.seed(0)
+    # single-process reference result (bypasses the process group on purpose)
+    _init = dist.is_initialized
+    dist.is_initialized = lambda: False
+    L1 = get_cluster_assignments_gpu(sargs, ds, m1, logger=None)
+    dist.is_initialized = _init
+    m2 = torch.nn.parallel.DistributedDataParallel(m1, device_ids=[local], find_unused_parameters=True)
+    margs = types.SimpleNamespace(**{**vars(sargs), "world_size": world, "rank": rank})
+    np.random.seed(0)
+    L2 = get_cluster_assignments_gpu(margs, ds, m2, logger=None)
+    same = bool(torch.equal(L1, L2))
+    print(f"[rank {rank}] sharded sweep labels == single-GPU labels: {same}", flush=True)
+    ok &= same
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
