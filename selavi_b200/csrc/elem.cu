@@ -168,18 +168,30 @@ __global__ void bn_bwd_reduce_kernel(const float4* __restrict__ g, const float4*
         const long long r0 = (long long)blockIdx.x * rows_per_block;
         long long r1 = r0 + rows_per_block;
         if (r1 > M) r1 = M;
-        for (long long r = r0 + warp; r < r1; r += 8) {
-            const size_t i = (size_t)r * c4n + c4;
-            const float4 zz = z[i];
-            float4 a = zz;
-            if (mask_mode == 1) a = act[i];
-            else if (mask_mode == 2) a = affine4(zz, sc, sh);
-            const float4 gg = masked_g(g[i], mask_mode, a);
-            s1.x += gg.x; s1.y += gg.y; s1.z += gg.z; s1.w += gg.w;
-            s2.x = fmaf(gg.x, (zz.x - mu.x) * is.x, s2.x);
-            s2.y = fmaf(gg.y, (zz.y - mu.y) * is.y, s2.y);
-            s2.z = fmaf(gg.z, (zz.z - mu.z) * is.z, s2.z);
-            s2.w = fmaf(gg.w, (zz.w - mu.w) * is.w, s2.w);
+        // 4 rows per iteration: 8-12 independent 16-byte loads in flight per thread (HBM-latency bound otherwise)
+        for (long long r = r0 + warp; r < r1; r += 32) {
+            float4 zz[4], gg[4], aa[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long rr = r + 8 * u;
+                const bool ok = rr < r1;
+                const size_t i = (size_t)(ok ? rr : r) * c4n + c4;
+                zz[u] = z[i];
+                gg[u] = g[i];
+                aa[u] = (mask_mode == 1) ? act[i] : zz[u];
+                if (!ok) gg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float4 a = aa[u];
+                if (mask_mode == 2) a = affine4(zz[u], sc, sh);
+                const float4 gm = masked_g(gg[u], mask_mode, a);
+                s1.x += gm.x; s1.y += gm.y; s1.z += gm.z; s1.w += gm.w;
+                s2.x = fmaf(gm.x, (zz[u].x - mu.x) * is.x, s2.x);
+                s2.y = fmaf(gm.y, (zz[u].y - mu.y) * is.y, s2.y);
+                s2.z = fmaf(gm.z, (zz[u].z - mu.z) * is.z, s2.z);
+                s2.w = fmaf(gm.w, (zz[u].w - mu.w) * is.w, s2.w);
+            }
         }
     }
     red[0][warp][lane] = s1;
@@ -201,36 +213,40 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* 
                                     const float4* __restrict__ act, int mask_mode, const float4* __restrict__ scale,
                                     const float4* __restrict__ shift, const float4* __restrict__ mean,
                                     const float4* __restrict__ invstd, const double* __restrict__ sums, double count,
-                                    long long M, int c4n, float4* __restrict__ dz, float4* __restrict__ gres,
+                                    long long total4, int c4n, float4* __restrict__ dz, float4* __restrict__ gres,
                                     int gres_accumulate, uint2* __restrict__ dz_hi, uint2* __restrict__ dz_lo) {
-    // grid (row blocks, ceil(c4n/32)), 256 threads: lane -> channel chunk (per-channel constants live in registers),
-    // warp -> row; dz = A*g + B*z + C with A = scale, B = -scale*invstd*m2, C = -scale*m1 + scale*invstd*m2*mean
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c4 = blockIdx.y * 32 + lane;
-    if (c4 >= c4n) return;
-    const int cs = c4n * 4, c = c4 * 4;
-    const float4 sc = __ldg(scale + c4), mu = __ldg(mean + c4), is = __ldg(invstd + c4);
-    float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (mask_mode == 2) sh = __ldg(shift + c4);
+    // dz = A*g + B*z + C per channel, A = scale, B = -scale*invstd*m2, C = -scale*m1 - B*mean (m1, m2 = sums / count);
+    // the coefficient table lives in shared memory, the element loop is a flat grid-stride stream (HBM-bound)
+    extern __shared__ float4 s_coef[];   // [3][c4n]: A | B | C   (+ [c4n] shift for mask_mode 2)
+    const int cs = c4n * 4;
     const double inv = 1.0 / count;
-    const float m1x = (float)(sums[c] * inv), m1y = (float)(sums[c + 1] * inv), m1z = (float)(sums[c + 2] * inv),
-                m1w = (float)(sums[c + 3] * inv);
-    const float m2x = (float)(sums[cs + c] * inv), m2y = (float)(sums[cs + c + 1] * inv), m2z = (float)(sums[cs + c + 2] * inv),
-                m2w = (float)(sums[cs + c + 3] * inv);
-    const float4 B = make_float4(-sc.x * is.x * m2x, -sc.y * is.y * m2y, -sc.z * is.z * m2z, -sc.w * is.w * m2w);
-    const float4 C = make_float4(-sc.x * m1x - B.x * mu.x, -sc.y * m1y - B.y * mu.y, -sc.z * m1z - B.z * mu.z,
-                                 -sc.w * m1w - B.w * mu.w);
-    const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
-    const long long r0 = (long long)blockIdx.x * rows_per_block;
-    long long r1 = r0 + rows_per_block;
-    if (r1 > M) r1 = M;
-    for (long long r = r0 + warp; r < r1; r += 8) {
-        const size_t i = (size_t)r * c4n + c4;
+    for (int c4 = threadIdx.x; c4 < c4n; c4 += blockDim.x) {
+        const float4 sc = __ldg(scale + c4), mu = __ldg(mean + c4), is = __ldg(invstd + c4);
+        const int c = c4 * 4;
+        const float m1x = (float)(sums[c] * inv), m1y = (float)(sums[c + 1] * inv), m1z = (float)(sums[c + 2] * inv),
+                    m1w = (float)(sums[c + 3] * inv);
+        const float m2x = (float)(sums[cs + c] * inv), m2y = (float)(sums[cs + c + 1] * inv),
+                    m2z = (float)(sums[cs + c + 2] * inv), m2w = (float)(sums[cs + c + 3] * inv);
+        const float4 B = make_float4(-sc.x * is.x * m2x, -sc.y * is.y * m2y, -sc.z * is.z * m2z, -sc.w * is.w * m2w);
+        s_coef[c4] = sc;
+        s_coef[c4n + c4] = B;
+        s_coef[2 * c4n + c4] = make_float4(-sc.x * m1x - B.x * mu.x, -sc.y * m1y - B.y * mu.y, -sc.z * m1z - B.z * mu.z,
+                                           -sc.w * m1w - B.w * mu.w);
+        s_coef[3 * c4n + c4] = (mask_mode == 2) ? __ldg(shift + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int cstep = (int)(stride % c4n);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int c4 = (int)(i % c4n);
+    for (; i < total4; i += stride) {
         const float4 zz = z[i];
+        const float4 sc = s_coef[c4];
         float4 a = zz;
         if (mask_mode == 1) a = act[i];
-        else if (mask_mode == 2) a = affine4(zz, sc, sh);
+        else if (mask_mode == 2) a = affine4(zz, sc, s_coef[3 * c4n + c4]);
         const float4 gg = masked_g(g[i], mask_mode, a);
+        const float4 B = s_coef[c4n + c4], C = s_coef[2 * c4n + c4];
         float4 o;
         o.x = fmaf(sc.x, gg.x, fmaf(B.x, zz.x, C.x));
         o.y = fmaf(sc.y, gg.y, fmaf(B.y, zz.y, C.y));
@@ -252,6 +268,8 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* 
             }
             gres[i] = rr;
         }
+        c4 += cstep;
+        if (c4 >= c4n) c4 -= c4n;
     }
 }
 
@@ -504,14 +522,10 @@ extern "C" int selavi_bn_bwd_apply(const float* g, const float* z, const float* 
     if (mask_mode == 1 && !act) return selavi_fail(-1, "bn_bwd_apply: mask_mode 1 needs act");
     if (mask_mode == 2 && !shift) return selavi_fail(-1, "bn_bwd_apply: mask_mode 2 needs shift");
     const int c4n = cs / 4;
-    long long nblk = (M + 31) / 32;
-    const long long cap = (148LL * 16) / ((c4n + 31) / 32);
-    if (nblk > cap) nblk = cap;
-    if (nblk < 1) nblk = 1;
-    dim3 grid((unsigned)nblk, (c4n + 31) / 32);
-    bn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+    const long long total4 = M * c4n;
+    bn_bwd_apply_kernel<<<ew_blocks(total4), EW_THREADS, (size_t)4 * c4n * sizeof(float4), (cudaStream_t)stream>>>(
         (const float4*)g, (const float4*)z, (const float4*)act, mask_mode, (const float4*)scale, (const float4*)shift,
-        (const float4*)mean, (const float4*)invstd, sums, count, M, c4n, (float4*)dz, (float4*)gres, gres_accumulate,
+        (const float4*)mean, (const float4*)invstd, sums, count, total4, c4n, (float4*)dz, (float4*)gres, gres_accumulate,
         (uint2*)dz_hi, (uint2*)dz_lo);
     LAUNCH_CHECK("bn_bwd_apply");
     return 0;
