@@ -97,6 +97,20 @@ int selavi_dgrad_pack_weights(const float* W, const int* geom, int co, void* wpa
 int selavi_conv_dgrad_bf16(const void* z_hi, const void* z_lo, float* dx, const void* wpack, const int* geom,
                            int accumulate, int passes, void* stream);
 
+/* Tap-reuse ("halo") forward convolution in fp16x3 for the stride-1 1x3x3 / 3x1x1 (and 2-D 3x3) convolutions of
+ * tv:video/resnet.py:45-61 and tv:resnet.py:59-105: the input window of a 128-pixel tile is normalised, split and
+ * staged in shared memory ONCE per 64-channel chunk and every tap reads it through a row-shifted UMMA descriptor
+ * (conv_gemm gathers and converts it once per tap).  Same contract as selavi_conv_gemm in mode 0 (fused BN+ReLU
+ * prologue, raw fp32 output, per-tile BN partial sums) except that stats_partial is [m_tiles][2][ntiles*bnt] with the
+ * tile counts returned by selavi_conv_halo_plan.  plan returns 0 when the geometry is supported, 1 when it is not
+ * (strided, other kernel shapes: use selavi_conv_gemm).  fp16 hi/lo operands carry 22 significant bits (as tf32x3);
+ * activations are pre-scaled by 2^4, weights by 2^8 (exact), |activation| must stay below 4094.
+ * flags: bit 0 = set the descriptor base-offset field for row-shifted windows (diagnostic; hardware wants 0). */
+int selavi_conv_halo_plan(const int* geom, int* m_tiles, int* bnt, int* ntiles, size_t* wpack_bytes);
+int selavi_conv_halo_pack_weights(const float* W, const int* geom, int ci, void* wpack, void* stream);
+int selavi_conv_halo_fwd(const float* src, float* dst, const void* wpack, const int* geom, const float* pro_scale,
+                         const float* pro_shift, int pro_relu, float* stats_partial, int flags, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm (train mode, nn.BatchNorm{1,2,3}d / SyncBatchNorm semantics), residual add, ReLU, pooling, layout,
  * SGD.  Activations channels-last fp32 [M, cs]; per-channel vectors have cs (padded) entries.

@@ -1,0 +1,592 @@
+// Tap-reuse ("halo") implicit-GEMM forward convolution on tcgen05 in fp16x3, for the stride-1 factorised convs of
+// R(2+1)D (tv:video/resnet.py:45-61: 1x3x3 spatial and 3x1x1 temporal, padding 1) and the 3x3 stride-1 convs of
+// the audio ResNet (tv:resnet.py:59-105) — the layers that dominate the forward of model.py:93-121.
+//
+// conv.cu gathers (and BN-normalises, splits, stores) every input element once PER TAP: 3x / 9x the loader work
+// and L2->SM traffic of the tensor itself, which is what bounds the N=64..144 layers of layer1.  Here a CTA
+// stages the input window of its 128 output pixels ONCE per 64-channel chunk as a linear array of 128-byte rows
+// (K-major, SWIZZLE_128B) and every tap is the same shared-memory tile read through a row-shifted descriptor:
+//   temporal: tile = 8 frames x 16 positions, slot row = (frame+1)*16 + position, tap kt shifts by 16*kt rows;
+//   spatial:  tile = 128 consecutive positions of the row-padded frame (pitch WP = W+2), slot row q = padded
+//             input index, tap (kh,kw) shifts by kh*WP + kw rows (the 2 junk columns per row are masked out).
+// Operands are fp16 hi/lo pairs (hi = fp16(x), lo = fp16(x - hi): 22 significant bits like the tf32x3 split, at
+// twice the MMA rate and half the shared-memory bytes); activations are pre-scaled by 2^4 and weights by 2^8 so
+// that the lo parts stay clear of the fp16 subnormal range, the epilogue multiplies by 2^-12 (all exact).
+// Loaders fuse the previous layer's train-mode BatchNorm+ReLU; the epilogue emits the BN partial sums (as conv.cu).
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "../../include/selavi_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int HL_EPI_WARPS = 4;
+constexpr int HL_LOADER_WARPS = 8;
+constexpr int HL_MMA_WARP = HL_EPI_WARPS + HL_LOADER_WARPS;
+constexpr int HL_BPROD_WARP = HL_MMA_WARP + 1;
+constexpr int HL_THREADS = (HL_BPROD_WARP + 1) * 32;
+constexpr int HL_MAX_A = 3;
+constexpr int HL_MAX_B = 8;
+constexpr float HL_ASCALE = 16.f;
+constexpr float HL_WSCALE = 256.f;
+constexpr float HL_OSCALE = 1.f / (16.f * 256.f);
+
+struct HaloParams {
+    const float* src;
+    float* dst;
+    const unsigned char* wpack;  // [ntile][kchunk][tap][hi|lo][bnt][128 B] fp16
+    const float* pro_scale;      // [cs] or null
+    const float* pro_shift;
+    float* stats;                // [m_tiles][2][ntiles*bnt] or null
+    int mode;                    // 0 temporal 3x1x1, 1 spatial 1x3x3
+    int nb, T, H, W, cs, cd;
+    int S, WP;
+    uint32_t wp_magic;           // ceil(2^32 / WP)
+    int TB, SB, OB;
+    int rows, rows_alloc;
+    int m_tiles, bnt, ntiles, kchunks, taps;
+    int n_a, n_b;
+    int pro_relu, use_base_off;
+    uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ void hl_st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void hl_named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint32_t hl_h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+// K-major SWIZZLE_128B descriptor of a window that starts at an arbitrary 128-byte row of a linear row array
+__device__ __forceinline__ uint64_t hl_desc(uint32_t saddr, int use_base_off) {
+    uint64_t d = sv::make_smem_desc_sw128(saddr, 16, 1024);
+    if (use_base_off) d |= static_cast<uint64_t>((saddr >> 7) & 7u) << 49;
+    return d;
+}
+
+struct HlBatch {
+    float4 v[4][2];
+    uint32_t ok;
+};
+
+__global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_plane = p.rows_alloc * 128;
+    const int a_slot_bytes = 2 * a_plane;
+    const int b_plane = p.bnt * 128;
+    const int b_slot_bytes = 2 * b_plane;
+    unsigned char* a_base = smem;
+    unsigned char* b_base = a_base + (size_t)p.n_a * a_slot_bytes;
+    unsigned char* tail = b_base + (size_t)p.n_b * b_slot_bytes;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* a_empty = a_full + HL_MAX_A;
+    uint64_t* b_full = a_empty + HL_MAX_A;
+    uint64_t* b_empty = b_full + HL_MAX_B;
+    uint64_t* tfull_bar = b_empty + HL_MAX_B;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);   // [EPI_WARPS][2][256]
+    float* s_pro = s_stat + HL_EPI_WARPS * 512;                 // [2][kchunks*64]: scale*16 | shift*16
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int total_tiles = p.m_tiles * p.ntiles;
+    const int ctab = p.kchunks * 64;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.n_a; ++s) {
+            sv::mbar_init(&a_full[s], HL_LOADER_WARPS);
+            sv::mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < p.n_b; ++s) {
+            sv::mbar_init(&b_full[s], 1);
+            sv::mbar_init(&b_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            sv::mbar_init(&tfull_bar[a], 1);
+            sv::mbar_init(&tempty_bar[a], HL_EPI_WARPS);
+        }
+        sv::fence_barrier_init();
+    }
+    for (int i = tid; i < ctab; i += HL_THREADS) {
+        float sc = HL_ASCALE, sf = 0.f;
+        if (p.pro_scale != nullptr) {
+            sc = i < p.cs ? p.pro_scale[i] * HL_ASCALE : 0.f;
+            sf = i < p.cs ? p.pro_shift[i] * HL_ASCALE : 0.f;
+        }
+        s_pro[i] = sc;
+        s_pro[ctab + i] = sf;
+    }
+    if (warp == HL_MMA_WARP) {
+        sv::tmem_alloc(tmem_slot, p.tmem_cols);
+        sv::tmem_relinquish();
+    }
+    sv::tc_fence_before();
+    __syncthreads();
+    sv::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= HL_EPI_WARPS && warp < HL_MMA_WARP) {
+        // ------------------------------------------------------------------ A loaders (256 threads)
+        const int ltid = tid - HL_EPI_WARPS * 32;
+        const int c = ltid & 7;        // 16-byte chunk (8 fp16 channels) of the 128-byte row
+        const int rbase = ltid >> 3;   // slot rows rbase + 32*j
+        const uint32_t sw_off = (uint32_t)((c ^ (rbase & 7)) << 4);
+        const int nrow_thr = p.rows_alloc >> 5;
+        const bool relu = p.pro_relu != 0;
+        int pb[8];
+        auto setup = [&](int tile) {
+            const int m_tile = tile / p.ntiles;
+            if (p.mode == 0) {
+                const int sb = m_tile % p.SB;
+                const int t1 = m_tile / p.SB;
+                const int tb = t1 % p.TB;
+                const int n = t1 / p.TB;
+                const int t0 = tb * 8 - 1, s0 = sb * 16;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = rbase + 32 * j;
+                    const int t = t0 + (r >> 4), s = s0 + (r & 15);
+                    const bool ok = (r < p.rows) & (t >= 0) & (t < p.T) & (s < p.S);
+                    pb[j] = ok ? (n * p.T + t) * p.S + s : -1;
+                }
+            } else {
+                const int ob = m_tile % p.OB;
+                const int f = m_tile / p.OB;
+                const int i0 = ob * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int q = rbase + 32 * j;
+                    const int i = i0 + q;
+                    const int hp = (int)__umulhi((uint32_t)i, p.wp_magic);
+                    const int wp = i - hp * p.WP;
+                    const bool ok = (q < p.rows) & (hp >= 1) & (hp <= p.H) & (wp >= 1) & (wp <= p.W);
+                    pb[j] = ok ? (f * p.H + hp - 1) * p.W + wp - 1 : -1;
+                }
+            }
+        };
+        auto gather = [&](HlBatch& b, const int jbase, int kc) {
+            const int ch = kc * 64 + c * 8;
+            const bool chan_ok = ch < p.cs;
+            b.ok = 0;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = jbase + jj;
+                b.v[jj][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                b.v[jj][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < nrow_thr && pb[j] >= 0 && chan_ok) {
+                    const float4* g = reinterpret_cast<const float4*>(p.src + (size_t)pb[j] * p.cs + ch);
+                    b.v[jj][0] = __ldg(g);
+                    b.v[jj][1] = __ldg(g + 1);
+                    b.ok |= 1u << jj;
+                }
+            }
+        };
+        auto commit = [&](const HlBatch& b, const int jbase, int kc, uint32_t a_hi) {
+            const uint32_t a_lo = a_hi + (uint32_t)a_plane;
+            const int ch = kc * 64 + c * 8;
+            const float4 sc0 = *reinterpret_cast<const float4*>(s_pro + ch);
+            const float4 sc1 = *reinterpret_cast<const float4*>(s_pro + ch + 4);
+            const float4 sf0 = *reinterpret_cast<const float4*>(s_pro + ctab + ch);
+            const float4 sf1 = *reinterpret_cast<const float4*>(s_pro + ctab + ch + 4);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = jbase + jj;
+                if (j < nrow_thr) {
+                    float x[8] = {b.v[jj][0].x, b.v[jj][0].y, b.v[jj][0].z, b.v[jj][0].w,
+                                  b.v[jj][1].x, b.v[jj][1].y, b.v[jj][1].z, b.v[jj][1].w};
+                    if ((b.ok >> jj) & 1u) {
+                        x[0] = fmaf(x[0], sc0.x, sf0.x);
+                        x[1] = fmaf(x[1], sc0.y, sf0.y);
+                        x[2] = fmaf(x[2], sc0.z, sf0.z);
+                        x[3] = fmaf(x[3], sc0.w, sf0.w);
+                        x[4] = fmaf(x[4], sc1.x, sf1.x);
+                        x[5] = fmaf(x[5], sc1.y, sf1.y);
+                        x[6] = fmaf(x[6], sc1.z, sf1.z);
+                        x[7] = fmaf(x[7], sc1.w, sf1.w);
+                        if (relu) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) x[e] = fmaxf(x[e], 0.f);
+                        }
+                    }
+                    uint32_t hb[4], lb[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __half2 h = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn(x[2 * e] - hf.x, x[2 * e + 1] - hf.y);
+                        hb[e] = hl_h2_bits(h);
+                        lb[e] = hl_h2_bits(l);
+                    }
+                    const uint32_t row_off = (uint32_t)((rbase + 32 * j) * 128) + sw_off;
+                    hl_st_shared_v4(a_hi + row_off, hb[0], hb[1], hb[2], hb[3]);
+                    hl_st_shared_v4(a_lo + row_off, lb[0], lb[1], lb[2], lb[3]);
+                }
+            }
+        };
+        int slot = 0;
+        uint32_t phase = 0;
+        int tile = blockIdx.x, kc = 0;
+        HlBatch sa, sb;
+        if (tile < total_tiles) {
+            setup(tile);
+            gather(sa, 0, 0);
+        }
+        while (tile < total_tiles) {
+            gather(sb, 4, kc);   // rows 4..7 of this slot in flight while rows 0..3 are converted
+            sv::mbar_wait(&a_empty[slot], phase ^ 1);
+            const uint32_t a_hi = sv::smem_u32(a_base + (size_t)slot * a_slot_bytes);
+            commit(sa, 0, kc, a_hi);
+            int ntile = tile, nkc = kc + 1;
+            if (nkc == p.kchunks) {
+                nkc = 0;
+                ntile += gridDim.x;
+            }
+            if (ntile < total_tiles) {
+                if (ntile != tile) setup(ntile);
+                gather(sa, 0, nkc);   // first rows of the NEXT slot in flight while rows 4..7 are converted
+            }
+            commit(sb, 4, kc, a_hi);
+            sv::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) sv::mbar_arrive(&a_full[slot]);
+            if (++slot == p.n_a) {
+                slot = 0;
+                phase ^= 1;
+            }
+            tile = ntile;
+            kc = nkc;
+        }
+    } else if (warp < HL_EPI_WARPS) {
+        // ------------------------------------------------------------------ epilogue (4 warps, one TMEM quadrant each)
+        const int quad = warp;
+        const int units = p.bnt >> 4;
+        const int ctot = p.ntiles * p.bnt;
+        float* my_stat = s_stat + (size_t)warp * 512;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const int m_tile = tile / p.ntiles, ntile = tile % p.ntiles;
+            const int m = quad * 32 + lane;
+            bool row_ok;
+            int pix;
+            if (p.mode == 0) {
+                const int sb = m_tile % p.SB;
+                const int t1 = m_tile / p.SB;
+                const int tb = t1 % p.TB;
+                const int n = t1 / p.TB;
+                const int t = tb * 8 + (m >> 4), s = sb * 16 + (m & 15);
+                row_ok = (t < p.T) & (s < p.S);
+                pix = (n * p.T + t) * p.S + s;
+            } else {
+                const int ob = m_tile % p.OB;
+                const int f = m_tile / p.OB;
+                const int o = ob * 128 + m;
+                const int h = (int)__umulhi((uint32_t)o, p.wp_magic);
+                const int w = o - h * p.WP;
+                row_ok = (h < p.H) & (w < p.W);
+                pix = (f * p.H + h) * p.W + w;
+            }
+            const int n_base = ntile * p.bnt;
+            float* out_row = p.dst + (size_t)(row_ok ? pix : 0) * p.cd;
+            sv::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
+            sv::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * (p.tmem_cols >> 1);
+            for (int u = 0; u < units; ++u) {
+                uint32_t av[16];
+                sv::tmem_ld16(taddr + (uint32_t)(u * 16), av);
+                sv::tmem_ld_wait();
+                float f[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = row_ok ? __uint_as_float(av[i]) * HL_OSCALE : 0.f;
+                const int ncol = n_base + u * 16;
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        if (ncol + i < p.cd)
+                            *reinterpret_cast<float4*>(out_row + ncol + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                    }
+                }
+                if (p.stats != nullptr) {
+                    // column sums over this warp's 32 rows (masked rows are exact zeros): transpose-reduce
+                    float s1[16], s2[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        s1[i] = f[i];
+                        s2[i] = f[i] * f[i];
+                    }
+#pragma unroll
+                    for (int off = 16, n = 8; off >= 2; off >>= 1, n >>= 1) {
+                        const bool upper = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (i < n) {
+                                const float send1 = upper ? s1[i] : s1[i + n];
+                                const float keep1 = upper ? s1[i + n] : s1[i];
+                                s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+                                const float send2 = upper ? s2[i] : s2[i + n];
+                                const float keep2 = upper ? s2[i + n] : s2[i];
+                                s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+                            }
+                        }
+                    }
+                    s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
+                    s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
+                    if ((lane & 1) == 0) {  // lane L holds column (L >> 1) of this unit
+                        my_stat[u * 16 + (lane >> 1)] = s1[0];
+                        my_stat[256 + u * 16 + (lane >> 1)] = s2[0];
+                    }
+                }
+            }
+            sv::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) sv::mbar_arrive(&tempty_bar[acc]);
+            if (p.stats != nullptr) {
+                hl_named_bar_sync(1, HL_EPI_WARPS * 32);
+                for (int i = tid; i < 2 * p.bnt; i += HL_EPI_WARPS * 32) {
+                    const int which = i >= p.bnt, col = which ? i - p.bnt : i;
+                    float tsum = 0.f;
+#pragma unroll
+                    for (int q = 0; q < HL_EPI_WARPS; ++q) tsum += s_stat[(size_t)q * 512 + which * 256 + col];
+                    p.stats[((size_t)m_tile * 2 + which) * ctot + n_base + col] = tsum;
+                }
+                hl_named_bar_sync(1, HL_EPI_WARPS * 32);
+            }
+        }
+    } else if (warp == HL_MMA_WARP) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idesc = sv::make_idesc_f16(128, p.bnt, 0, 0, 0, 0);  // fp16 x fp16, K-major
+            int sa = 0, sb = 0, it = 0;
+            uint32_t pa = 0, pbp = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                sv::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+                sv::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * (p.tmem_cols >> 1);
+                uint32_t first = 0;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    int nk16 = (p.cs - kc * 64 + 15) >> 4;
+                    if (nk16 > 4) nk16 = 4;
+                    sv::mbar_wait(&a_full[sa], pa);
+                    sv::tc_fence_after();
+                    const uint32_t a_hi = sv::smem_u32(a_base + (size_t)sa * a_slot_bytes);
+                    const uint32_t a_lo = a_hi + (uint32_t)a_plane;
+                    for (int tap = 0; tap < p.taps; ++tap) {
+                        const int shift_rows = p.mode == 0 ? tap * 16 : (tap / 3) * p.WP + (tap % 3);
+                        const uint32_t sh = (uint32_t)shift_rows * 128u;
+                        sv::mbar_wait(&b_full[sb], pbp);
+                        sv::tc_fence_after();
+                        const uint32_t b_hi = sv::smem_u32(b_base + (size_t)sb * b_slot_bytes);
+                        const uint32_t b_lo = b_hi + (uint32_t)b_plane;
+                        for (int k = 0; k < nk16; ++k) {
+                            const uint64_t da_hi = hl_desc(a_hi + sh + k * 32, p.use_base_off);
+                            const uint64_t da_lo = hl_desc(a_lo + sh + k * 32, p.use_base_off);
+                            const uint64_t db_hi = sv::make_smem_desc_sw128(b_hi + k * 32, 16, 1024);
+                            const uint64_t db_lo = sv::make_smem_desc_sw128(b_lo + k * 32, 16, 1024);
+                            sv::umma_f16(d_tmem, da_lo, db_hi, idesc, first);
+                            sv::umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+                            sv::umma_f16(d_tmem, da_hi, db_hi, idesc, 1u);
+                            first = 1u;
+                        }
+                        sv::umma_commit(&b_empty[sb]);
+                        if (++sb == p.n_b) {
+                            sb = 0;
+                            pbp ^= 1;
+                        }
+                    }
+                    sv::umma_commit(&a_empty[sa]);
+                    if (++sa == p.n_a) {
+                        sa = 0;
+                        pa ^= 1;
+                    }
+                }
+                sv::umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ B producer (one thread, TMA bulk)
+        if (lane == 0) {
+            int sb = 0;
+            uint32_t pbp = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int ntile = tile % p.ntiles;
+                const unsigned char* wsrc = p.wpack + (size_t)ntile * p.kchunks * p.taps * b_slot_bytes;
+                const int nslots = p.kchunks * p.taps;
+                for (int i = 0; i < nslots; ++i) {
+                    sv::mbar_wait(&b_empty[sb], pbp ^ 1);
+                    sv::mbar_arrive_expect_tx(&b_full[sb], (uint32_t)b_slot_bytes);
+                    sv::bulk_g2s(b_base + (size_t)sb * b_slot_bytes, wsrc + (size_t)i * b_slot_bytes, (uint32_t)b_slot_bytes,
+                                 &b_full[sb]);
+                    if (++sb == p.n_b) {
+                        sb = 0;
+                        pbp ^= 1;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == HL_MMA_WARP) {
+        sv::tc_fence_after();
+        sv::tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// W (torch layout [co][ci][taps]) -> fp16 hi/lo B tiles [ntile][kchunk][tap][hi|lo][bnt rows][128 B], scaled by 2^8.
+__global__ void conv_halo_pack_kernel(const float* __restrict__ W, int co, int ci, int taps, int bnt, int ntiles, int kchunks,
+                                      __half* __restrict__ out) {
+    const size_t total = (size_t)ntiles * kchunks * taps * bnt * 64;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(idx & 7);
+        const int c = (int)((idx >> 3) & 7);
+        const int n = (int)((idx >> 6) % bnt);
+        const size_t blk = (idx >> 6) / bnt;  // (ntile*kchunks + kc)*taps + tap
+        const int tap = (int)(blk % taps);
+        const int kc = (int)((blk / taps) % kchunks);
+        const int nt = (int)(blk / taps / kchunks);
+        const int k = kc * 64 + c * 8 + e;
+        const int nn = nt * bnt + n;
+        float val = 0.f;
+        if (nn < co && k < ci) val = W[((size_t)nn * ci + k) * taps + tap] * HL_WSCALE;
+        const __half hi = __float2half_rn(val);
+        const __half lo = __float2half_rn(val - __half2float(hi));
+        __half* base = out + blk * (size_t)(2 * bnt * 64);
+        const int pos = n * 64 + ((c ^ (n & 7)) << 3) + e;
+        base[pos] = hi;
+        base[bnt * 64 + pos] = lo;
+    }
+}
+
+struct HaloPlan {
+    int mode, nb, T, H, W, cs, cd, co, ci;
+    int S, WP, TB, SB, OB, rows, rows_alloc, m_tiles, bnt, ntiles, kchunks, taps, n_a, n_b;
+    size_t smem, wbytes;
+};
+
+// geom: the 20-int forward geometry of selavi_conv_gemm.  Returns 0 when the halo kernel supports it, 1 otherwise.
+int hl_plan(const int* g, HaloPlan* pl) {
+    if (g[0] != 0) return 1;
+    const int nb = g[1], ts = g[2], hs = g[3], ws = g[4], cs = g[5], td = g[6], hd = g[7], wd = g[8], cd = g[9];
+    const int kt = g[10], kh = g[11], kw = g[12], st = g[13], sh = g[14], sw = g[15], pt = g[16], ph = g[17], pw = g[18];
+    if (st != 1 || sh != 1 || sw != 1) return 1;
+    if (ts != td || hs != hd || ws != wd) return 1;
+    if ((cs & 7) || (cd & 7) || cs <= 0 || cd <= 0) return 1;
+    int mode;
+    if (kt == 3 && kh == 1 && kw == 1 && pt == 1 && ph == 0 && pw == 0) mode = 0;
+    else if (kt == 1 && kh == 3 && kw == 3 && pt == 0 && ph == 1 && pw == 1) mode = 1;
+    else return 1;
+    pl->mode = mode;
+    pl->nb = nb; pl->T = ts; pl->H = hs; pl->W = ws; pl->cs = cs; pl->cd = cd; pl->co = g[19];
+    pl->S = hs * ws;
+    pl->WP = ws + 2;
+    pl->taps = mode == 0 ? 3 : 9;
+    pl->kchunks = (cs + 63) / 64;
+    const long long pixels = (long long)nb * ts * hs * ws;
+    if (pixels <= 0 || pixels > 0x7fffffffLL) return 1;
+    if (mode == 0) {
+        pl->TB = (ts + 7) / 8;
+        pl->SB = (pl->S + 15) / 16;
+        pl->OB = 0;
+        pl->rows = 160;
+        const long long mt = (long long)nb * pl->TB * pl->SB;
+        if (mt > 0x3fffffffLL) return 1;
+        pl->m_tiles = (int)mt;
+    } else {
+        if (pl->WP > 62) return 1;   // slot rows 128 + 2*WP + 2 must fit 256
+        if ((long long)(hs + 2) * pl->WP + 256 > 60000) return 1;   // exactness range of the magic division
+        pl->TB = pl->SB = 0;
+        pl->OB = (hs * pl->WP + 127) / 128;
+        pl->rows = 128 + 2 * pl->WP + 2;
+        const long long mt = (long long)nb * ts * pl->OB;
+        if (mt > 0x3fffffffLL) return 1;
+        pl->m_tiles = (int)mt;
+    }
+    pl->rows_alloc = (pl->rows + 31) & ~31;
+    const int a_slot = 2 * pl->rows_alloc * 128;
+    const int fixed = (2 * HL_MAX_A + 2 * HL_MAX_B + 4) * 8 + 16 + HL_EPI_WARPS * 512 * 4 + 2 * pl->kchunks * 64 * 4 + 1024 + 64;
+    const int budget = 227 * 1024 - fixed;
+    for (int nt = (cd + 255) / 256; nt <= 16; ++nt) {
+        int per = (cd + nt - 1) / nt;
+        per = (per + 15) & ~15;
+        const int b_slot = 2 * per * 128;
+        int n_a = 2;
+        int n_b = (budget - n_a * a_slot) / b_slot;
+        if (n_b < 2) continue;
+        if (n_b > HL_MAX_B) n_b = HL_MAX_B;
+        if (n_b >= 4 && budget - 3 * a_slot - 4 * b_slot >= 0) {   // room for a third A slot
+            n_a = 3;
+            n_b = (budget - n_a * a_slot) / b_slot;
+            if (n_b > HL_MAX_B) n_b = HL_MAX_B;
+        }
+        pl->bnt = per;
+        pl->ntiles = nt;
+        pl->n_a = n_a;
+        pl->n_b = n_b;
+        pl->smem = (size_t)n_a * a_slot + (size_t)n_b * b_slot + fixed;
+        pl->wbytes = (size_t)nt * pl->kchunks * pl->taps * b_slot;
+        return 0;
+    }
+    return 1;
+}
+
+}  // namespace
+
+extern "C" int selavi_conv_halo_plan(const int* geom, int* m_tiles, int* bnt, int* ntiles, size_t* wpack_bytes) {
+    if (!geom) return selavi_fail(-1, "conv_halo_plan: null geometry");
+    HaloPlan pl;
+    if (hl_plan(geom, &pl) != 0) return 1;
+    if (m_tiles) *m_tiles = pl.m_tiles;
+    if (bnt) *bnt = pl.bnt;
+    if (ntiles) *ntiles = pl.ntiles;
+    if (wpack_bytes) *wpack_bytes = pl.wbytes;
+    return 0;
+}
+
+extern "C" int selavi_conv_halo_pack_weights(const float* W, const int* geom, int ci, void* wpack, void* stream) {
+    if (!W || !geom || !wpack || ci <= 0) return selavi_fail(-1, "conv_halo_pack_weights: bad arguments");
+    HaloPlan pl;
+    if (hl_plan(geom, &pl) != 0) return selavi_fail(-1, "conv_halo_pack_weights: geometry not supported by the halo kernel");
+    const size_t total = (size_t)pl.ntiles * pl.kchunks * pl.taps * pl.bnt * 64;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    conv_halo_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, pl.co, ci, pl.taps, pl.bnt, pl.ntiles, pl.kchunks,
+                                                                    reinterpret_cast<__half*>(wpack));
+    SV_CUDA_CHECK(cudaGetLastError(), "conv_halo_pack_weights: launch");
+    return 0;
+}
+
+extern "C" int selavi_conv_halo_fwd(const float* src, float* dst, const void* wpack, const int* geom, const float* pro_scale,
+                                    const float* pro_shift, int pro_relu, float* stats_partial, int flags, void* stream) {
+    if (!src || !dst || !wpack || !geom) return selavi_fail(-1, "conv_halo_fwd: null argument");
+    if ((pro_scale == nullptr) != (pro_shift == nullptr)) return selavi_fail(-1, "conv_halo_fwd: prologue needs scale and shift");
+    HaloPlan pl;
+    if (hl_plan(geom, &pl) != 0) return selavi_fail(-1, "conv_halo_fwd: geometry not supported by the halo kernel");
+    HaloParams p;
+    p.src = src; p.dst = dst; p.wpack = reinterpret_cast<const unsigned char*>(wpack);
+    p.pro_scale = pro_scale; p.pro_shift = pro_shift; p.stats = stats_partial;
+    p.mode = pl.mode; p.nb = pl.nb; p.T = pl.T; p.H = pl.H; p.W = pl.W; p.cs = pl.cs; p.cd = pl.cd;
+    p.S = pl.S; p.WP = pl.WP;
+    p.wp_magic = (uint32_t)((0x100000000ULL + (unsigned)pl.WP - 1) / (unsigned)pl.WP);
+    p.TB = pl.TB; p.SB = pl.SB; p.OB = pl.OB; p.rows = pl.rows; p.rows_alloc = pl.rows_alloc;
+    p.m_tiles = pl.m_tiles; p.bnt = pl.bnt; p.ntiles = pl.ntiles; p.kchunks = pl.kchunks; p.taps = pl.taps;
+    p.n_a = pl.n_a; p.n_b = pl.n_b;
+    p.pro_relu = pro_relu;
+    p.use_base_off = (flags & 1) ? 1 : 0;
+    uint32_t cols = 32;
+    while ((int)cols < 2 * p.bnt) cols <<= 1;
+    p.tmem_cols = cols;
+    SV_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem),
+                  "conv_halo_fwd: cudaFuncSetAttribute");
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int total_tiles = p.m_tiles * p.ntiles;
+    const int grid = total_tiles < sms ? total_tiles : sms;
+    conv_halo_kernel<<<grid, HL_THREADS, pl.smem, (cudaStream_t)stream>>>(p);
+    SV_CUDA_CHECK(cudaGetLastError(), "conv_halo_fwd: launch");
+    return 0;
+}

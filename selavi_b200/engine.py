@@ -96,7 +96,11 @@ def _packed(conv, geom, mode):
     hit = cache.get(mode)
     if hit is not None and hit[0] == tag:
         return hit[1]
-    buf = ops.pack_weights(weight, geom, mode, out=hit[1] if (hit is not None and hit[1].device == weight.device) else None)
+    prev = hit[1] if (hit is not None and hit[1].device == weight.device) else None
+    if isinstance(mode, tuple):
+        buf = ops.pack_weights_halo(weight, geom, out=prev)
+    else:
+        buf = ops.pack_weights(weight, geom, mode, out=prev)
     cache[mode] = (tag, buf)
     return buf
 
@@ -121,15 +125,20 @@ class TowerRunner:
         x = act.t
         nb, t, h, w, _ = x.shape
         geom = _geom_of(conv, nb, (t, h, w))
-        wp = _packed(conv, geom, 0)
+        plan = ops.halo_plan(geom) if PASSES == 3 else None
+        halo = plan is not None
+        wp = _packed(conv, geom, ("halo", plan[1], plan[2]) if halo else 0)
         dev = x.device
         cs = geom.cos
         scale = torch.empty(cs, dtype=torch.float32, device=dev)
         shift = torch.empty(cs, dtype=torch.float32, device=dev)
         rec = None
         if training:
-            stats = ops.stats_buffer(geom, dev)
-            z = ops.conv_forward(x, wp, geom, scale=act.scale, shift=act.shift, relu=act.relu, stats=stats, passes=PASSES)
+            stats = ops.stats_buffer(geom, dev, halo=halo)
+            if halo:
+                z = ops.conv_forward_halo(x, wp, geom, scale=act.scale, shift=act.shift, relu=act.relu, stats=stats)
+            else:
+                z = ops.conv_forward(x, wp, geom, scale=act.scale, shift=act.shift, relu=act.relu, stats=stats, passes=PASSES)
             sums = torch.empty(2 * cs, dtype=torch.float64, device=dev)
             _lib.check(lib.selavi_bn_reduce_partials(_lib.ptr(stats), stats.shape[0], stats.shape[2], cs, _lib.ptr(sums),
                                                      _stream()), "selavi_bn_reduce_partials")
@@ -154,7 +163,10 @@ class TowerRunner:
                 rec.conv, rec.bn, rec.geom, rec.inp, rec.z = conv, bn, geom, act, z
                 rec.scale, rec.shift, rec.mean, rec.invstd, rec.count = scale, shift, mean, invstd, count
         else:
-            z = ops.conv_forward(x, wp, geom, scale=act.scale, shift=act.shift, relu=act.relu, stats=None, passes=PASSES)
+            if halo:
+                z = ops.conv_forward_halo(x, wp, geom, scale=act.scale, shift=act.shift, relu=act.relu, stats=None)
+            else:
+                z = ops.conv_forward(x, wp, geom, scale=act.scale, shift=act.shift, relu=act.relu, stats=None, passes=PASSES)
             _lib.check(lib.selavi_bn_eval_affine(_lib.ptr(bn.weight), _lib.ptr(bn.bias), _lib.ptr(bn.running_mean),
                                                  _lib.ptr(bn.running_var), bn.eps, geom.co, cs, _lib.ptr(scale),
                                                  _lib.ptr(shift), _stream()), "selavi_bn_eval_affine")

@@ -132,7 +132,74 @@ def pack_weights(w, geom, mode, out=None):
     return out
 
 
-def stats_buffer(geom, device):
+# Forward kernel selection: "auto" = tap-reuse fp16x3 kernel (conv_halo.cu) where it is supported and pays
+# (stride-1 3x1x1 / 1x3x3 convs with enough frames / wide enough rows), tf32x3 implicit GEMM (conv.cu) elsewhere;
+# "igemm" = conv.cu everywhere; "halo" = conv_halo.cu wherever the geometry is supported.
+import os as _os
+FWD_KERNEL = _os.environ.get("SELAVI_FWD_KERNEL", "auto")
+HALO_FLAGS = int(_os.environ.get("SELAVI_HALO_FLAGS", "0"))
+
+
+def halo_plan(geom):
+    """-> (m_tiles, bnt, ntiles, wpack_bytes) of the tap-reuse forward kernel, or None when it does not apply."""
+    cached = geom.__dict__.get("_halo")
+    if cached is not None:
+        return cached or None
+    plan = False
+    if FWD_KERNEL != "igemm":
+        mt, bnt, nt, wb = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
+        code = _lib.lib().selavi_conv_halo_plan(geom.arr(0), ctypes.byref(mt), ctypes.byref(bnt), ctypes.byref(nt),
+                                                ctypes.byref(wb))
+        if code < 0:
+            _lib.check(code, "selavi_conv_halo_plan")
+        if code == 0:
+            pays = True
+            if FWD_KERNEL == "auto":
+                # measured on B200 (tools/quick_bench.py halo, profiles/r01g_halo_microbench.txt): ~2x over the tf32x3
+                # implicit GEMM on every R(2+1)D-18 layer except the 7x7 spatial convs of layer4, where only W/(W+2)
+                # = 78 % of the MMA rows and 49/63 of each frame's last tile are useful
+                if geom.kt == 1:
+                    pays = geom.wi >= 12
+            if pays:
+                plan = (mt.value, bnt.value, nt.value, wb.value)
+    geom.__dict__["_halo"] = plan
+    return plan or None
+
+
+def pack_weights_halo(w, geom, out=None):
+    """torch weight -> fp16 hi/lo per-tap B tiles of the tap-reuse forward kernel."""
+    w = w.detach()
+    if not (w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()):
+        raise ValueError("weight must be a contiguous fp32 CUDA tensor")
+    plan = halo_plan(geom)
+    if plan is None:
+        raise ValueError("geometry not supported by the halo kernel")
+    if out is None:
+        out = torch.empty(plan[3], dtype=torch.uint8, device=w.device)
+    elif out.numel() != plan[3]:
+        raise ValueError("packed weight buffer has the wrong size")
+    with _Guard(w.device):
+        _lib.check(_lib.lib().selavi_conv_halo_pack_weights(_lib.ptr(w), geom.arr(0), geom.ci, _lib.ptr(out), _lib.stream_ptr()),
+                   "selavi_conv_halo_pack_weights")
+    return out
+
+
+def conv_forward_halo(x, wpack, geom, out=None, scale=None, shift=None, relu=False, stats=None):
+    _chk(x, geom.in_shape(), "x")
+    if out is None:
+        out = torch.empty(geom.out_shape(), dtype=torch.float32, device=x.device)
+    _chk(out, geom.out_shape(), "out")
+    with _Guard(x.device), _Prof("conv_fwd", geom):
+        _lib.check(_lib.lib().selavi_conv_halo_fwd(_lib.ptr(x), _lib.ptr(out), _lib.ptr(wpack), geom.arr(0), _lib.ptr(scale),
+                                                   _lib.ptr(shift), 1 if relu else 0, _lib.ptr(stats), HALO_FLAGS,
+                                                   _lib.stream_ptr()), "selavi_conv_halo_fwd")
+    return out
+
+
+def stats_buffer(geom, device, halo=False):
+    if halo:
+        mt, bnt, nt, _ = halo_plan(geom)
+        return torch.empty((mt, 2, bnt * nt), dtype=torch.float32, device=device)
     bnt, nt = conv_tiles(geom.co)
     return torch.empty(((geom.m_out + 127) // 128, 2, bnt * nt), dtype=torch.float32, device=device)
 

@@ -134,3 +134,71 @@ def test_conv_dgrad_bf16x3(cuda_device, name):
     dw = torch.empty_like(w)
     ops.conv_wgrad_bf16(ops.to_channels_last(x), z_hi, z_lo, geom, dw)
     assert _rel(dw, ref_dw) < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ tap-reuse forward
+# name: (nb, ci, co, (T,H,W), kernel): stride 1, padding 1 along the 3-wide dims (the halo kernel's domain)
+HALO_LAYERS = {
+    "t_l1": (1, 144, 64, (8, 28, 28), (3, 1, 1)),            # 2.25 K chunks, N=64
+    "t_ragged": (2, 45, 64, (5, 9, 7), (3, 1, 1)),           # T < 8, S % 16 != 0, one partial K chunk
+    "t_l2_230": (1, 230, 128, (16, 14, 14), (3, 1, 1)),      # cs=232: last k16 half valid, two frame blocks
+    "t_l3_two_ntiles": (1, 64, 460, (8, 8, 8), (3, 1, 1)),   # two N tiles
+    "s_l1": (1, 64, 144, (2, 56, 56), (1, 3, 3)),            # WP=58: 246 slot rows
+    "s_ragged": (2, 24, 40, (3, 11, 13), (1, 3, 3)),         # last tile of the frame partial, cs=24
+    "s_l2_128_230": (1, 128, 230, (2, 28, 28), (1, 3, 3)),   # two K chunks, cd=232
+    "s_audio_2d": (2, 64, 64, (1, 65, 50), (1, 3, 3)),       # 2-D conv (T=1)
+}
+
+
+def _mk_halo(name, device):
+    from selavi_b200 import ops
+    nb, ci, co, thw, k = HALO_LAYERS[name]
+    p = (1, 0, 0) if k[0] == 3 else (0, 1, 1)
+    g = torch.Generator(device=device).manual_seed(hash(name) % 1000)
+    x = torch.randn(nb, ci, *thw, device=device, generator=g)
+    w = torch.randn(co, ci, *k, device=device, generator=g) * (1.0 / (ci * k[0] * k[1] * k[2]) ** 0.5)
+    return x, w, ops.ConvGeom(nb, ci, co, thw, k, (1, 1, 1), p), p
+
+
+@pytest.mark.parametrize("name", sorted(HALO_LAYERS))
+def test_conv_forward_halo(cuda_device, name, monkeypatch):
+    """fp16x3 tap-reuse kernel vs float64 conv: same 5e-5 bar as the tf32x3 kernel (22-bit operands, fp32 accumulate)."""
+    from selavi_b200 import ops
+    monkeypatch.setattr(ops, "FWD_KERNEL", "halo")
+    x, w, geom, p = _mk_halo(name, cuda_device)
+    assert ops.halo_plan(geom) is not None
+    ref = F.conv3d(x.double(), w.double(), None, 1, p)
+    y = ops.conv_forward_halo(ops.to_channels_last(x), ops.pack_weights_halo(w, geom), geom)
+    if geom.cos > geom.co:
+        assert y[..., geom.co:].abs().max().item() == 0
+    err = _rel(ops.from_channels_last(y, geom.co), ref)
+    print(f"{name} halo fwd rel={err:.3e}")
+    assert err < 5e-5
+
+
+@pytest.mark.parametrize("name", sorted(HALO_LAYERS))
+def test_conv_forward_halo_prologue_and_stats(cuda_device, name, monkeypatch):
+    from selavi_b200 import ops
+    monkeypatch.setattr(ops, "FWD_KERNEL", "halo")
+    x, w, geom, p = _mk_halo(name, cuda_device)
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    scale = torch.rand(geom.cis, device=cuda_device, generator=g) + 0.5
+    shift = torch.randn(geom.cis, device=cuda_device, generator=g) * 0.3
+    xn = torch.relu(x.double() * scale[:geom.ci].double().view(1, -1, 1, 1, 1) + shift[:geom.ci].double().view(1, -1, 1, 1, 1))
+    ref = F.conv3d(xn, w.double(), None, 1, p)
+    stats = ops.stats_buffer(geom, cuda_device, halo=True)
+    y = ops.conv_forward_halo(ops.to_channels_last(x), ops.pack_weights_halo(w, geom), geom, scale=scale, shift=shift,
+                              relu=True, stats=stats)
+    assert _rel(ops.from_channels_last(y, geom.co), ref) < 5e-5
+    tot = stats.double().sum(0)[:, :geom.co]
+    l1 = ref.abs().sum((0, 2, 3, 4))
+    assert float(((tot[0] - ref.sum((0, 2, 3, 4))).abs() / l1).max()) < 1e-5
+    assert float(((tot[1] - (ref * ref).sum((0, 2, 3, 4))).abs() / (ref * ref).sum((0, 2, 3, 4))).max()) < 1e-4
+
+
+def test_halo_plan_rejects_other_geometries(cuda_device, monkeypatch):
+    from selavi_b200 import ops
+    monkeypatch.setattr(ops, "FWD_KERNEL", "halo")
+    for name in ("v_stem0_7x7", "v_l2_spatial_s2", "v_l2_temporal_s2", "v_l2_downsample", "ragged_m"):
+        nb, ci, co, thw, k, s, p = LAYERS[name]
+        assert ops.halo_plan(ops.ConvGeom(nb, ci, co, thw, k, s, p)) is None

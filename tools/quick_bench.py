@@ -62,10 +62,48 @@ def bench_conv(name, nb, ci, co, thw, k, s, p):
               f"  wgrad {mswb:.3f} ms ({flop / mswb / 1e9:.1f})", flush=True)
 
 
+def bench_halo(name, nb, ci, co, thw, k):
+    """tap-reuse fp16x3 forward vs the tf32x3 implicit GEMM on the same layer (with the fused BN+ReLU prologue)"""
+    ops.FWD_KERNEL = "halo"
+    p = (1, 0, 0) if k[0] == 3 else (0, 1, 1)
+    geom = ops.ConvGeom(nb, ci, co, thw, k, (1, 1, 1), p)
+    x = torch.randn(geom.in_shape(), device=dev)
+    w = torch.randn(co, ci, *k, device=dev) * 0.05
+    sc = torch.rand(geom.cis, device=dev) + 0.5
+    sf = torch.randn(geom.cis, device=dev) * 0.3
+    y = torch.empty(geom.out_shape(), device=dev)
+    flop = 2.0 * geom.m_out * co * ci * geom.taps
+    wp = ops.pack_weights(w, geom, 0)
+    st = ops.stats_buffer(geom, dev)
+    ms0 = timeit(lambda: ops.conv_forward(x, wp, geom, out=y, scale=sc, shift=sf, relu=True, stats=st, passes=3))
+    y0 = y.clone()
+    plan = ops.halo_plan(geom)
+    wph = ops.pack_weights_halo(w, geom)
+    sth = ops.stats_buffer(geom, dev, halo=True)
+    ms1 = timeit(lambda: ops.conv_forward_halo(x, wph, geom, out=y, scale=sc, shift=sf, relu=True, stats=sth))
+    rel = float((y - y0).norm() / y0.norm())
+    byts = (x.numel() + y.numel()) * 4
+    print(f"{name}: igemm tf32x3 {ms0:.3f} ms ({flop / ms0 / 1e9:.1f} TF/s) | halo fp16x3 {ms1:.3f} ms ({flop / ms1 / 1e9:.1f} TF/s, "
+          f"{byts / ms1 / 1e6:.0f} GB/s in+out) plan(m_tiles,bnt,nt,wbytes)={plan} rel diff {rel:.2e}", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "sk"):
         bench_sk()
+    if what == "halo":
+        bench_halo("l1_temporal 144->64", 16, 144, 64, (32, 56, 56), (3, 1, 1))
+        bench_halo("l1_spatial 64->144", 16, 64, 144, (32, 56, 56), (1, 3, 3))
+        bench_halo("stem_t 45->64", 16, 45, 64, (32, 56, 56), (3, 1, 1))
+        bench_halo("l2_spatial 128->230", 16, 128, 230, (16, 28, 28), (1, 3, 3))
+        bench_halo("l2_temporal 230->128", 16, 230, 128, (16, 28, 28), (3, 1, 1))
+        bench_halo("l2_spatial 128->288", 16, 128, 288, (16, 28, 28), (1, 3, 3))
+        bench_halo("l2_temporal 288->128", 16, 288, 128, (16, 28, 28), (3, 1, 1))
+        bench_halo("l3_spatial 256->576", 16, 256, 576, (8, 14, 14), (1, 3, 3))
+        bench_halo("l3_temporal 576->256", 16, 576, 256, (8, 14, 14), (3, 1, 1))
+        bench_halo("l4_spatial 512->1152", 16, 512, 1152, (4, 7, 7), (1, 3, 3))
+        bench_halo("l4_temporal 1152->512", 16, 1152, 512, (4, 7, 7), (3, 1, 1))
+        bench_halo("audio_l1 64->64", 16, 64, 64, (1, 65, 50), (1, 3, 3))
     if what in ("all", "conv"):
         bench_conv("l1_spatial", 16, 64, 144, (32, 56, 56), (1, 3, 3), (1, 1, 1), (0, 1, 1))
         bench_conv("l1_temporal", 16, 144, 64, (32, 56, 56), (3, 1, 1), (1, 1, 1), (1, 0, 0))
