@@ -107,9 +107,15 @@ int selavi_conv_dgrad_bf16(const void* z_hi, const void* z_lo, float* dx, const 
  * activations are pre-scaled by 2^4, weights by 2^8 (exact), |activation| must stay below 4094.
  * flags: bit 0 = set the descriptor base-offset field for row-shifted windows (diagnostic; hardware wants 0). */
 int selavi_conv_halo_plan(const int* geom, int* m_tiles, int* bnt, int* ntiles, size_t* wpack_bytes);
-int selavi_conv_halo_pack_weights(const float* W, const int* geom, int ci, void* wpack, void* stream);
+int selavi_conv_halo_pack_weights(const float* W, const int* geom, int k_real, void* wpack, void* stream);
 int selavi_conv_halo_fwd(const float* src, float* dst, const void* wpack, const int* geom, const float* pro_scale,
                          const float* pro_shift, int pro_relu, float* stats_partial, int flags, void* stream);
+/* Data gradient of the same convolutions with the same kernel (geom in mode 1; for stride 1 the gradient is the
+ * convolution of dz with flipped taps and the transposed weight matrix): z_hi/z_lo = bf16 hi/lo planes of dz as for
+ * selavi_conv_dgrad_bf16, copied into the tile by cp.async, bf16x3 MMAs, dx written or accumulated.  wpack from
+ * selavi_conv_halo_pack_weights with the mode-1 geometry (k_real = co; forward: k_real = ci). */
+int selavi_conv_halo_dgrad(const void* z_hi, const void* z_lo, float* dx, const void* wpack, const int* geom,
+                           int accumulate, int flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm (train mode, nn.BatchNorm{1,2,3}d / SyncBatchNorm semantics), residual add, ReLU, pooling, layout,

@@ -13,6 +13,12 @@
 // twice the MMA rate and half the shared-memory bytes); activations are pre-scaled by 2^4 and weights by 2^8 so
 // that the lo parts stay clear of the fp16 subnormal range, the epilogue multiplies by 2^-12 (all exact).
 // Loaders fuse the previous layer's train-mode BatchNorm+ReLU; the epilogue emits the BN partial sums (as conv.cu).
+//
+// The same kernel computes the DATA GRADIENT of these convolutions (loss.backward(), main.py:298): for stride 1 it
+// is the same convolution of dz with the taps flipped and the weight matrix transposed.  dz arrives as bf16 hi/lo
+// planes (written by the BatchNorm-backward kernel), so in that mode the loaders are pure 16-byte cp.async copies
+// and the MMAs run in bf16x3 without scaling (gradients need the bf16 exponent range).
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
 
@@ -34,7 +40,9 @@ constexpr float HL_WSCALE = 256.f;
 constexpr float HL_OSCALE = 1.f / (16.f * 256.f);
 
 struct HaloParams {
-    const float* src;
+    const float* src;            // src_kind 0: fp32 activations (normalised / split to fp16 hi/lo by the loaders)
+    const __nv_bfloat16* src_hi; // src_kind 1: pre-split bf16 planes (copied by cp.async)
+    const __nv_bfloat16* src_lo;
     float* dst;
     const unsigned char* wpack;  // [ntile][kchunk][tap][hi|lo][bnt][128 B] fp16
     const float* pro_scale;      // [cs] or null
@@ -49,8 +57,14 @@ struct HaloParams {
     int m_tiles, bnt, ntiles, kchunks, taps;
     int n_a, n_b;
     int pro_relu, use_base_off;
+    int src_kind, accumulate;
+    float oscale;
     uint32_t tmem_cols;
 };
+
+__device__ __forceinline__ void hl_cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 
 __device__ __forceinline__ void hl_st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -230,7 +244,51 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
         int slot = 0;
         uint32_t phase = 0;
         int tile = blockIdx.x, kc = 0;
+        if (p.src_kind == 1) {
+            // pre-split bf16 planes: the slot is filled by zero-filling 16-byte cp.async copies, published one slot late
+            int prev_slot = -1;
+            while (tile < total_tiles) {
+                if (kc == 0) setup(tile);
+                sv::mbar_wait(&a_empty[slot], phase ^ 1);
+                const uint32_t a_hi = sv::smem_u32(a_base + (size_t)slot * a_slot_bytes);
+                const uint32_t a_lo = a_hi + (uint32_t)a_plane;
+                const int ch = kc * 64 + c * 8;
+                const bool chan_ok = ch < p.cs;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < nrow_thr) {
+                        const bool ok = chan_ok && pb[j] >= 0;
+                        const size_t goff = ok ? (size_t)pb[j] * p.cs + ch : 0;
+                        const uint32_t nbytes = ok ? 16u : 0u;
+                        const uint32_t row_off = (uint32_t)((rbase + 32 * j) * 128) + sw_off;
+                        hl_cp_async16(a_hi + row_off, p.src_hi + goff, nbytes);
+                        hl_cp_async16(a_lo + row_off, p.src_lo + goff, nbytes);
+                    }
+                }
+                asm volatile("cp.async.commit_group;\n" ::: "memory");
+                if (prev_slot >= 0) {
+                    asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+                    sv::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) sv::mbar_arrive(&a_full[prev_slot]);
+                }
+                prev_slot = slot;
+                if (++slot == p.n_a) {
+                    slot = 0;
+                    phase ^= 1;
+                }
+                if (++kc == p.kchunks) {
+                    kc = 0;
+                    tile += gridDim.x;
+                }
+            }
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            sv::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && prev_slot >= 0) sv::mbar_arrive(&a_full[prev_slot]);
+        }
         HlBatch sa, sb;
+        if (p.src_kind == 1) tile = total_tiles;
         if (tile < total_tiles) {
             setup(tile);
             gather(sa, 0, 0);
@@ -301,13 +359,23 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
                 sv::tmem_ld_wait();
                 float f[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = row_ok ? __uint_as_float(av[i]) * HL_OSCALE : 0.f;
+                for (int i = 0; i < 16; ++i) f[i] = row_ok ? __uint_as_float(av[i]) * p.oscale : 0.f;
                 const int ncol = n_base + u * 16;
                 if (row_ok) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
-                        if (ncol + i < p.cd)
-                            *reinterpret_cast<float4*>(out_row + ncol + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                        if (ncol + i < p.cd) {
+                            float4* dp = reinterpret_cast<float4*>(out_row + ncol + i);
+                            float4 o = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                            if (p.accumulate) {
+                                const float4 old = *dp;
+                                o.x += old.x;
+                                o.y += old.y;
+                                o.z += old.z;
+                                o.w += old.w;
+                            }
+                            *dp = o;
+                        }
                     }
                 }
                 if (p.stats != nullptr) {
@@ -359,7 +427,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
     } else if (warp == HL_MMA_WARP) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
-            const uint32_t idesc = sv::make_idesc_f16(128, p.bnt, 0, 0, 0, 0);  // fp16 x fp16, K-major
+            const int fmt = p.src_kind == 1 ? 1 : 0;   // fp16 x fp16 (forward) or bf16 x bf16 (data gradient), K-major
+            const uint32_t idesc = sv::make_idesc_f16(128, p.bnt, fmt, fmt, 0, 0);
             int sa = 0, sb = 0, it = 0;
             uint32_t pa = 0, pbp = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -437,8 +506,10 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
 }
 
 // W (torch layout [co][ci][taps]) -> fp16 hi/lo B tiles [ntile][kchunk][tap][hi|lo][bnt rows][128 B], scaled by 2^8.
-__global__ void conv_halo_pack_kernel(const float* __restrict__ W, int co, int ci, int taps, int bnt, int ntiles, int kchunks,
-                                      __half* __restrict__ out) {
+//   mode 0 (forward):       n = co, k = ci, tap as is
+//   mode 1 (data gradient): n = ci, k = co, tap flipped (taps-1-tap), bf16 hi/lo, unscaled
+__global__ void conv_halo_pack_kernel(const float* __restrict__ W, int mode, int co, int ci, int taps, int bnt, int ntiles,
+                                      int kchunks, uint16_t* __restrict__ out) {
     const size_t total = (size_t)ntiles * kchunks * taps * bnt * 64;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int e = (int)(idx & 7);
@@ -451,10 +522,21 @@ __global__ void conv_halo_pack_kernel(const float* __restrict__ W, int co, int c
         const int k = kc * 64 + c * 8 + e;
         const int nn = nt * bnt + n;
         float val = 0.f;
-        if (nn < co && k < ci) val = W[((size_t)nn * ci + k) * taps + tap] * HL_WSCALE;
-        const __half hi = __float2half_rn(val);
-        const __half lo = __float2half_rn(val - __half2float(hi));
-        __half* base = out + blk * (size_t)(2 * bnt * 64);
+        uint16_t hi, lo;
+        if (mode == 0) {
+            if (nn < co && k < ci) val = W[((size_t)nn * ci + k) * taps + tap] * HL_WSCALE;
+            const __half h = __float2half_rn(val);
+            const __half l = __float2half_rn(val - __half2float(h));
+            hi = __half_as_ushort(h);
+            lo = __half_as_ushort(l);
+        } else {
+            if (nn < ci && k < co) val = W[((size_t)k * ci + nn) * taps + (taps - 1 - tap)];
+            const __nv_bfloat16 h = __float2bfloat16_rn(val);
+            const __nv_bfloat16 l = __float2bfloat16_rn(val - __bfloat162float(h));
+            hi = __bfloat16_as_ushort(h);
+            lo = __bfloat16_as_ushort(l);
+        }
+        uint16_t* base = out + blk * (size_t)(2 * bnt * 64);
         const int pos = n * 64 + ((c ^ (n & 7)) << 3) + e;
         base[pos] = hi;
         base[bnt * 64 + pos] = lo;
@@ -467,9 +549,10 @@ struct HaloPlan {
     size_t smem, wbytes;
 };
 
-// geom: the 20-int forward geometry of selavi_conv_gemm.  Returns 0 when the halo kernel supports it, 1 otherwise.
+// geom: the 20-int geometry of selavi_conv_gemm (mode 0 forward, mode 1 data gradient: for these stride-1 "same"
+// convolutions both are the same gather with cs / cd swapped).  Returns 0 when the halo kernel supports it, 1 otherwise.
 int hl_plan(const int* g, HaloPlan* pl) {
-    if (g[0] != 0) return 1;
+    if (g[0] != 0 && g[0] != 1) return 1;
     const int nb = g[1], ts = g[2], hs = g[3], ws = g[4], cs = g[5], td = g[6], hd = g[7], wd = g[8], cd = g[9];
     const int kt = g[10], kh = g[11], kw = g[12], st = g[13], sh = g[14], sw = g[15], pt = g[16], ph = g[17], pw = g[18];
     if (st != 1 || sh != 1 || sw != 1) return 1;
@@ -546,47 +629,74 @@ extern "C" int selavi_conv_halo_plan(const int* geom, int* m_tiles, int* bnt, in
     return 0;
 }
 
-extern "C" int selavi_conv_halo_pack_weights(const float* W, const int* geom, int ci, void* wpack, void* stream) {
-    if (!W || !geom || !wpack || ci <= 0) return selavi_fail(-1, "conv_halo_pack_weights: bad arguments");
+extern "C" int selavi_conv_halo_pack_weights(const float* W, const int* geom, int k_real, void* wpack, void* stream) {
+    if (!W || !geom || !wpack || k_real <= 0) return selavi_fail(-1, "conv_halo_pack_weights: bad arguments");
     HaloPlan pl;
     if (hl_plan(geom, &pl) != 0) return selavi_fail(-1, "conv_halo_pack_weights: geometry not supported by the halo kernel");
     const size_t total = (size_t)pl.ntiles * pl.kchunks * pl.taps * pl.bnt * 64;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    conv_halo_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, pl.co, ci, pl.taps, pl.bnt, pl.ntiles, pl.kchunks,
-                                                                    reinterpret_cast<__half*>(wpack));
+    // forward: W[co = n_out][ci = k_real];  data gradient: W[co = k_real][ci = n_out]
+    const int co = geom[0] == 0 ? pl.co : k_real, ci = geom[0] == 0 ? k_real : pl.co;
+    conv_halo_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, geom[0], co, ci, pl.taps, pl.bnt, pl.ntiles, pl.kchunks,
+                                                                    reinterpret_cast<uint16_t*>(wpack));
     SV_CUDA_CHECK(cudaGetLastError(), "conv_halo_pack_weights: launch");
     return 0;
 }
 
+static int hl_launch(const HaloPlan& pl, HaloParams& p, int flags, void* stream);
+
 extern "C" int selavi_conv_halo_fwd(const float* src, float* dst, const void* wpack, const int* geom, const float* pro_scale,
                                     const float* pro_shift, int pro_relu, float* stats_partial, int flags, void* stream) {
     if (!src || !dst || !wpack || !geom) return selavi_fail(-1, "conv_halo_fwd: null argument");
+    if (geom[0] != 0) return selavi_fail(-1, "conv_halo_fwd: geometry must be in forward mode");
     if ((pro_scale == nullptr) != (pro_shift == nullptr)) return selavi_fail(-1, "conv_halo_fwd: prologue needs scale and shift");
     HaloPlan pl;
     if (hl_plan(geom, &pl) != 0) return selavi_fail(-1, "conv_halo_fwd: geometry not supported by the halo kernel");
     HaloParams p;
-    p.src = src; p.dst = dst; p.wpack = reinterpret_cast<const unsigned char*>(wpack);
+    p.src = src; p.src_hi = nullptr; p.src_lo = nullptr; p.dst = dst; p.wpack = reinterpret_cast<const unsigned char*>(wpack);
     p.pro_scale = pro_scale; p.pro_shift = pro_shift; p.stats = stats_partial;
+    p.pro_relu = pro_relu;
+    p.src_kind = 0; p.accumulate = 0; p.oscale = HL_OSCALE;
+    return hl_launch(pl, p, flags, stream);
+}
+
+extern "C" int selavi_conv_halo_dgrad(const void* z_hi, const void* z_lo, float* dx, const void* wpack, const int* geom,
+                                      int accumulate, int flags, void* stream) {
+    if (!z_hi || !z_lo || !dx || !wpack || !geom) return selavi_fail(-1, "conv_halo_dgrad: null argument");
+    if (geom[0] != 1) return selavi_fail(-1, "conv_halo_dgrad: geometry must be in dgrad mode");
+    HaloPlan pl;
+    if (hl_plan(geom, &pl) != 0) return selavi_fail(-1, "conv_halo_dgrad: geometry not supported by the halo kernel");
+    HaloParams p;
+    p.src = nullptr;
+    p.src_hi = reinterpret_cast<const __nv_bfloat16*>(z_hi);
+    p.src_lo = reinterpret_cast<const __nv_bfloat16*>(z_lo);
+    p.dst = dx; p.wpack = reinterpret_cast<const unsigned char*>(wpack);
+    p.pro_scale = nullptr; p.pro_shift = nullptr; p.stats = nullptr;
+    p.pro_relu = 0;
+    p.src_kind = 1; p.accumulate = accumulate ? 1 : 0; p.oscale = 1.f;
+    return hl_launch(pl, p, flags, stream);
+}
+
+static int hl_launch(const HaloPlan& pl, HaloParams& p, int flags, void* stream) {
     p.mode = pl.mode; p.nb = pl.nb; p.T = pl.T; p.H = pl.H; p.W = pl.W; p.cs = pl.cs; p.cd = pl.cd;
     p.S = pl.S; p.WP = pl.WP;
     p.wp_magic = (uint32_t)((0x100000000ULL + (unsigned)pl.WP - 1) / (unsigned)pl.WP);
     p.TB = pl.TB; p.SB = pl.SB; p.OB = pl.OB; p.rows = pl.rows; p.rows_alloc = pl.rows_alloc;
     p.m_tiles = pl.m_tiles; p.bnt = pl.bnt; p.ntiles = pl.ntiles; p.kchunks = pl.kchunks; p.taps = pl.taps;
     p.n_a = pl.n_a; p.n_b = pl.n_b;
-    p.pro_relu = pro_relu;
     p.use_base_off = (flags & 1) ? 1 : 0;
     uint32_t cols = 32;
     while ((int)cols < 2 * p.bnt) cols <<= 1;
     p.tmem_cols = cols;
     SV_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem),
-                  "conv_halo_fwd: cudaFuncSetAttribute");
+                  "conv_halo: cudaFuncSetAttribute");
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int total_tiles = p.m_tiles * p.ntiles;
     const int grid = total_tiles < sms ? total_tiles : sms;
     conv_halo_kernel<<<grid, HL_THREADS, pl.smem, (cudaStream_t)stream>>>(p);
-    SV_CUDA_CHECK(cudaGetLastError(), "conv_halo_fwd: launch");
+    SV_CUDA_CHECK(cudaGetLastError(), "conv_halo: launch");
     return 0;
 }

@@ -98,7 +98,7 @@ def _packed(conv, geom, mode):
         return hit[1]
     prev = hit[1] if (hit is not None and hit[1].device == weight.device) else None
     if isinstance(mode, tuple):
-        buf = ops.pack_weights_halo(weight, geom, out=prev)
+        buf = ops.pack_weights_halo(weight, geom, out=prev, mode=1 if mode[0] == "halo_dgrad" else 0)
     else:
         buf = ops.pack_weights(weight, geom, mode, out=prev)
     cache[mode] = (tag, buf)
@@ -300,6 +300,10 @@ class TowerRunner:
         if not want_dx:
             return None
         if bf16:
+            plan = ops.halo_plan(geom, 1) if PASSES == 3 else None
+            if plan is not None:
+                return ops.conv_dgrad_halo(z_hi, z_lo, _packed(conv, geom, ("halo_dgrad", plan[1], plan[2])), geom, out=dx_out,
+                                           accumulate=dx_accumulate)
             return ops.conv_dgrad_bf16(z_hi, z_lo, _packed_dgrad_bf16(conv, geom), geom, out=dx_out, accumulate=dx_accumulate,
                                        passes=3 if PASSES == 3 else 1)
         wpt = _packed(conv, geom, 1)

@@ -140,15 +140,17 @@ FWD_KERNEL = _os.environ.get("SELAVI_FWD_KERNEL", "auto")
 HALO_FLAGS = int(_os.environ.get("SELAVI_HALO_FLAGS", "0"))
 
 
-def halo_plan(geom):
-    """-> (m_tiles, bnt, ntiles, wpack_bytes) of the tap-reuse forward kernel, or None when it does not apply."""
-    cached = geom.__dict__.get("_halo")
+def halo_plan(geom, mode=0):
+    """-> (m_tiles, bnt, ntiles, wpack_bytes) of the tap-reuse kernel (mode 0 forward, 1 data gradient), or None when
+    it does not apply."""
+    key = "_halo%d" % mode
+    cached = geom.__dict__.get(key)
     if cached is not None:
         return cached or None
     plan = False
     if FWD_KERNEL != "igemm":
         mt, bnt, nt, wb = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
-        code = _lib.lib().selavi_conv_halo_plan(geom.arr(0), ctypes.byref(mt), ctypes.byref(bnt), ctypes.byref(nt),
+        code = _lib.lib().selavi_conv_halo_plan(geom.arr(mode), ctypes.byref(mt), ctypes.byref(bnt), ctypes.byref(nt),
                                                 ctypes.byref(wb))
         if code < 0:
             _lib.check(code, "selavi_conv_halo_plan")
@@ -162,16 +164,16 @@ def halo_plan(geom):
                     pays = geom.wi >= 12
             if pays:
                 plan = (mt.value, bnt.value, nt.value, wb.value)
-    geom.__dict__["_halo"] = plan
+    geom.__dict__[key] = plan
     return plan or None
 
 
-def pack_weights_halo(w, geom, out=None):
-    """torch weight -> fp16 hi/lo per-tap B tiles of the tap-reuse forward kernel."""
+def pack_weights_halo(w, geom, out=None, mode=0):
+    """torch weight -> per-tap hi/lo B tiles of the tap-reuse kernel (mode 0: fp16, forward; mode 1: bf16, data gradient)."""
     w = w.detach()
     if not (w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()):
         raise ValueError("weight must be a contiguous fp32 CUDA tensor")
-    plan = halo_plan(geom)
+    plan = halo_plan(geom, mode)
     if plan is None:
         raise ValueError("geometry not supported by the halo kernel")
     if out is None:
@@ -179,8 +181,22 @@ def pack_weights_halo(w, geom, out=None):
     elif out.numel() != plan[3]:
         raise ValueError("packed weight buffer has the wrong size")
     with _Guard(w.device):
-        _lib.check(_lib.lib().selavi_conv_halo_pack_weights(_lib.ptr(w), geom.arr(0), geom.ci, _lib.ptr(out), _lib.stream_ptr()),
-                   "selavi_conv_halo_pack_weights")
+        _lib.check(_lib.lib().selavi_conv_halo_pack_weights(_lib.ptr(w), geom.arr(mode), geom.ci if mode == 0 else geom.co,
+                                                            _lib.ptr(out), _lib.stream_ptr()), "selavi_conv_halo_pack_weights")
+    return out
+
+
+def conv_dgrad_halo(z_hi, z_lo, wpack, geom, out=None, accumulate=False):
+    _chk_bf16(z_hi, geom.out_shape(), "z_hi")
+    _chk_bf16(z_lo, geom.out_shape(), "z_lo")
+    if out is None:
+        out = torch.empty(geom.in_shape(), dtype=torch.float32, device=z_hi.device)
+        accumulate = False
+    _chk(out, geom.in_shape(), "dx")
+    with _Guard(z_hi.device), _Prof("conv_dgrad", geom):
+        _lib.check(_lib.lib().selavi_conv_halo_dgrad(_lib.ptr(z_hi), _lib.ptr(z_lo), _lib.ptr(out), _lib.ptr(wpack), geom.arr(1),
+                                                     1 if accumulate else 0, HALO_FLAGS, _lib.stream_ptr()),
+                   "selavi_conv_halo_dgrad")
     return out
 
 

@@ -202,3 +202,26 @@ def test_halo_plan_rejects_other_geometries(cuda_device, monkeypatch):
     for name in ("v_stem0_7x7", "v_l2_spatial_s2", "v_l2_temporal_s2", "v_l2_downsample", "ragged_m"):
         nb, ci, co, thw, k, s, p = LAYERS[name]
         assert ops.halo_plan(ops.ConvGeom(nb, ci, co, thw, k, s, p)) is None
+
+
+@pytest.mark.parametrize("name", sorted(HALO_LAYERS))
+def test_conv_dgrad_halo(cuda_device, name, monkeypatch):
+    """data gradient through the tap-reuse kernel (bf16x3 on pre-split planes, flipped taps) vs float64 autograd"""
+    from selavi_b200 import ops
+    monkeypatch.setattr(ops, "FWD_KERNEL", "halo")
+    x, w, geom, p = _mk_halo(name, cuda_device)
+    assert ops.halo_plan(geom, 1) is not None
+    xd = x.double().requires_grad_(True)
+    ref_y = F.conv3d(xd, w.double(), None, 1, p)
+    dz = torch.randn(ref_y.shape, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(7))
+    ref_dx, = torch.autograd.grad(ref_y, xd, dz.double())
+    z_hi, z_lo = ops.split_bf16(ops.to_channels_last(dz))
+    wp = ops.pack_weights_halo(w, geom, mode=1)
+    dx = ops.conv_dgrad_halo(z_hi, z_lo, wp, geom)
+    if geom.cis > geom.ci:
+        assert dx[..., geom.ci:].abs().max().item() == 0
+    err = _rel(ops.from_channels_last(dx, geom.ci), ref_dx)
+    print(f"{name} halo dgrad rel={err:.3e}")
+    assert err < 5e-5
+    dx2 = ops.conv_dgrad_halo(z_hi, z_lo, wp, geom, out=dx.clone(), accumulate=True)
+    assert _rel(dx2, 2 * dx) < 1e-6

@@ -82,6 +82,18 @@ def bench_halo(name, nb, ci, co, thw, k):
     sth = ops.stats_buffer(geom, dev, halo=True)
     ms1 = timeit(lambda: ops.conv_forward_halo(x, wph, geom, out=y, scale=sc, shift=sf, relu=True, stats=sth))
     rel = float((y - y0).norm() / y0.norm())
+    # data gradient: cp.async-fed bf16x3 implicit GEMM vs the same through the tap-reuse kernel
+    dz = torch.randn(geom.out_shape(), device=dev)
+    z_hi, z_lo = ops.split_bf16(dz)
+    dx = torch.empty(geom.in_shape(), device=dev)
+    wpb = ops.pack_weights_dgrad_bf16(w, geom)
+    msd0 = timeit(lambda: ops.conv_dgrad_bf16(z_hi, z_lo, wpb, geom, out=dx))
+    dx0 = dx.clone()
+    wpd = ops.pack_weights_halo(w, geom, mode=1)
+    msd1 = timeit(lambda: ops.conv_dgrad_halo(z_hi, z_lo, wpd, geom, out=dx))
+    reld = float((dx - dx0).norm() / dx0.norm())
+    print(f"{name}: dgrad bf16x3 igemm {msd0:.3f} ms ({flop / msd0 / 1e9:.1f} TF/s) | halo {msd1:.3f} ms ({flop / msd1 / 1e9:.1f} TF/s) "
+          f"rel diff {reld:.2e}", flush=True)
     byts = (x.numel() + y.numel()) * 4
     print(f"{name}: igemm tf32x3 {ms0:.3f} ms ({flop / ms0 / 1e9:.1f} TF/s) | halo fp16x3 {ms1:.3f} ms ({flop / ms1 / 1e9:.1f} TF/s, "
           f"{byts / ms1 / 1e6:.0f} GB/s in+out) plan(m_tiles,bnt,nt,wbytes)={plan} rel diff {rel:.2e}", flush=True)
