@@ -217,27 +217,47 @@ def run_ours(args):
     prof, ops.PROFILE = ops.PROFILE, None
     agg = {}
     if os.environ.get("SELAVI_BENCH_DETAIL") and rank == 0:
-        for kind, flops, e0, e1, tag in prof:
+        for kind, flops, e0, e1, tag, kern in prof:
             ms = e0.elapsed_time(e1)
-            print(f"DETAIL {kind:11s} ci,co,T,H,W,k,s={tag} {ms:8.3f} ms {flops / ms / 1e9:7.1f} TF/s", file=sys.stderr)
-    for kind, flops, e0, e1, _tag in prof:
-        a = agg.setdefault(kind, [0.0, 0.0, 0])
+            print(f"DETAIL {kind:11s} ci,co,T,H,W,k,s={tag} {ms:8.3f} ms {flops / ms / 1e9:7.1f} TF/s  {kern}", file=sys.stderr)
+    for _kind, flops, e0, e1, _tag, kern in prof:
+        a = agg.setdefault(kern, [0.0, 0.0, 0])
         a[0] += flops
         a[1] += e0.elapsed_time(e1)
         a[2] += 1
     ms_step = ms_total / args.steps
-    conv = [agg.get("conv_fwd", [0, 0, 0]), agg.get("conv_dgrad", [0, 0, 0])]
-    conv_flops, conv_ms, conv_n = sum(c[0] for c in conv), sum(c[1] for c in conv), sum(c[2] for c in conv)
-    wg = agg.get("conv_wgrad", [0.0, 0.0, 0])
-    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     from selavi_b200 import engine
-    roofline = {"kernel": "conv_igemm_kernel (forward + data-gradient launches)", "bound": "tensor", "achieved": achieved,
-                "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"], "traffic": None,
-                "peak_source": f"{pk['src']} bf16 dense sustained", "launches_per_step": conv_n,
-                "avg_launch_ms": conv_ms / max(conv_n, 1), "share_of_step": conv_ms / ms_step,
-                "mma_passes": engine.PASSES, "issued_mma_tflops": achieved * engine.PASSES,
-                "wgrad_kernel": {"achieved": (wg[0] / (wg[1] * 1e-3) / 1e12) if wg[1] > 0 else 0.0, "unit": "TFLOP/s",
-                                 "launches_per_step": wg[2], "share_of_step": wg[1] / ms_step}}
+    # per kernel: algorithmic conv FLOPs (2*M*Co*Ci*taps) / launch time, CUDA events on the launching
+    # stream.  The x3 operand split issues 3 MMAs per algorithmic MAC, so `issued_mma_tflops` = 3x achieved; the fp16x3 /
+    # bf16x3 kernels run at the bf16 rate (ceiling 1/3 of the peak below), the tf32x3 kernels at half of it (ceiling 1/6).
+    kernels = {}
+    for kern, (fl, ms, n) in agg.items():
+        ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        kernels[kern] = {"achieved": ach, "unit": "TFLOP/s", "frac": ach / pk["tensor"], "issued_mma_tflops": ach * engine.PASSES,
+                         "launches_per_step": n, "avg_launch_ms": ms / max(n, 1), "ms_per_step": ms, "share_of_step": ms / ms_step}
+    top = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
+    conv_ms = sum(k["ms_per_step"] for k in kernels.values())
+    conv_fl = sum(a[0] for a in agg.values())
+    roofline = {"kernel": top, "bound": "tensor", "achieved": kernels[top]["achieved"] if top else 0.0,
+                "peak": pk["tensor"], "unit": "TFLOP/s", "frac": kernels[top]["frac"] if top else 0.0, "traffic": None,
+                "peak_source": f"{pk['src']} bf16 dense sustained", "launches_per_step": kernels[top]["launches_per_step"] if top else 0,
+                "avg_launch_ms": kernels[top]["avg_launch_ms"] if top else 0.0,
+                "share_of_step": kernels[top]["share_of_step"] if top else 0.0,
+                "mma_passes": engine.PASSES, "issued_mma_tflops": kernels[top]["issued_mma_tflops"] if top else 0.0,
+                "all_conv_kernels": {"achieved": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0, "unit": "TFLOP/s",
+                                     "share_of_step": conv_ms / ms_step},
+                "per_kernel": kernels}
+
+    # DRAM bytes per launch of the reported kernels, from the committed ncu --set full captures (profiles/ncu_traffic.json)
+    traffic = {}
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f)
+    except (OSError, ValueError):
+        pass
+    if top and isinstance(traffic.get(top), dict):
+        roofline["traffic"] = traffic[top].get("bytes")
+        roofline["traffic_launch"] = traffic[top].get("launch")
 
     # ---- Sinkhorn-Knopp: cfg-5 matrix, rows sharded over ranks, exactly 100 iterations (convergence test computed)
     sk = None
@@ -265,7 +285,9 @@ def run_ours(args):
         gbs = bytes_iter * iters / (ms_sk * 1e-3) / 1e9
         sk = {"iters_per_sec": iters / (ms_sk * 1e-3), "N": n_local * world, "K": K, "iters": iters, "rows_per_gpu": n_local,
               "roofline": {"kernel": "sk_kernel", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
-                           "frac": gbs / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+                           "frac": gbs / pk["hbm"], "peak_source": pk["src"],
+                           "traffic": (traffic.get("sk_kernel") or {}).get("bytes") if world == 1 else None,
+                           "algorithmic_bytes_per_launch": bytes_iter * iters,
                            "note": "per GPU; shards below ~126 MB are L2-resident, so frac can exceed 1"}}
     except Exception as e:  # noqa: BLE001
         sk = {"error": repr(e)[:300]}
@@ -275,7 +297,7 @@ def run_ours(args):
         value = global_batch / (ms_step * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "tf32x3 (fp32-accurate split tf32 MMA, fp32 accumulate/storage)" if engine.PASSES == 3 else "tf32",
+                "vs_baseline": None, "dtype": "f32 (operands split hi/lo: fp16x3 / tf32x3 forward, bf16x3 backward MMAs; fp32 accumulate and storage)" if engine.PASSES == 3 else "tf32",
                 "data": "synthetic",
                 "config": {"workload": "configs[1]: train step (video R(2+1)D-18 + audio ResNet-9 fwd/bwd, 20 MLP heads, CE, SGD), "
                                        "per-GPU batch 16, clips 3x32x112x112, spectrograms 1x257x200, K=309, 10 heads",

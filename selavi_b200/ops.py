@@ -35,9 +35,10 @@ PROFILE = None
 
 
 class _Prof:
-    def __init__(self, kind, geom):
+    def __init__(self, kind, geom, kernel):
         self.on = PROFILE is not None
         if self.on:
+            self.kernel = kernel
             self.kind, self.flops = kind, 2.0 * geom.m_out * geom.co * geom.ci * geom.taps
             self.tag = (geom.ci, geom.co, geom.ti, geom.hi, geom.wi, geom.kt, geom.kh, geom.kw, geom.st, geom.sh)
             self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -49,7 +50,7 @@ class _Prof:
     def __exit__(self, *a):
         if self.on:
             self.e1.record()
-            PROFILE.append((self.kind, self.flops, self.e0, self.e1, self.tag))
+            PROFILE.append((self.kind, self.flops, self.e0, self.e1, self.tag, self.kernel))
 
 
 def padc(c):
@@ -160,8 +161,14 @@ def halo_plan(geom, mode=0):
                 # measured on B200 (tools/quick_bench.py halo, profiles/r01g_halo_microbench.txt): ~2x over the tf32x3
                 # implicit GEMM on every R(2+1)D-18 layer except the 7x7 spatial convs of layer4, where only W/(W+2)
                 # = 78 % of the MMA rows and 49/63 of each frame's last tile are useful
-                if geom.kt == 1:
-                    pays = geom.wi >= 12
+                if mode == 0:
+                    pays = geom.kt == 3 or geom.wi >= 12
+                else:
+                    # data gradient (cp.async-fed in both kernels): the tap-reuse kernel wins on the temporal convs with
+                    # at least one full 8-frame block (1.3-2.1x) and on the small-frame spatial convs (1.1-1.7x); on the
+                    # 56x56 / 28x28 spatial convs both are bound by streaming the weight tiles from L2 and the implicit
+                    # GEMM's exact K packing is ~5 % ahead
+                    pays = geom.ti >= 8 if geom.kt == 3 else geom.wi <= 14
             if pays:
                 plan = (mt.value, bnt.value, nt.value, wb.value)
     geom.__dict__[key] = plan
@@ -193,7 +200,7 @@ def conv_dgrad_halo(z_hi, z_lo, wpack, geom, out=None, accumulate=False):
         out = torch.empty(geom.in_shape(), dtype=torch.float32, device=z_hi.device)
         accumulate = False
     _chk(out, geom.in_shape(), "dx")
-    with _Guard(z_hi.device), _Prof("conv_dgrad", geom):
+    with _Guard(z_hi.device), _Prof("conv_dgrad", geom, "conv_halo_kernel[dgrad bf16x3]"):
         _lib.check(_lib.lib().selavi_conv_halo_dgrad(_lib.ptr(z_hi), _lib.ptr(z_lo), _lib.ptr(out), _lib.ptr(wpack), geom.arr(1),
                                                      1 if accumulate else 0, HALO_FLAGS, _lib.stream_ptr()),
                    "selavi_conv_halo_dgrad")
@@ -205,7 +212,7 @@ def conv_forward_halo(x, wpack, geom, out=None, scale=None, shift=None, relu=Fal
     if out is None:
         out = torch.empty(geom.out_shape(), dtype=torch.float32, device=x.device)
     _chk(out, geom.out_shape(), "out")
-    with _Guard(x.device), _Prof("conv_fwd", geom):
+    with _Guard(x.device), _Prof("conv_fwd", geom, "conv_halo_kernel[fwd fp16x3]"):
         _lib.check(_lib.lib().selavi_conv_halo_fwd(_lib.ptr(x), _lib.ptr(out), _lib.ptr(wpack), geom.arr(0), _lib.ptr(scale),
                                                    _lib.ptr(shift), 1 if relu else 0, _lib.ptr(stats), HALO_FLAGS,
                                                    _lib.stream_ptr()), "selavi_conv_halo_fwd")
@@ -230,7 +237,7 @@ def conv_forward(x, wpack, geom, out=None, scale=None, shift=None, relu=False, s
     if out is None:
         out = torch.empty(geom.out_shape(), dtype=torch.float32, device=x.device)
     _chk(out, geom.out_shape(), "out")
-    with _Guard(x.device), _Prof("conv_fwd", geom):
+    with _Guard(x.device), _Prof("conv_fwd", geom, "conv_igemm_kernel[fwd tf32x3]"):
         _lib.check(_lib.lib().selavi_conv_gemm(_lib.ptr(x), _lib.ptr(out), _lib.ptr(wpack), geom.arr(0), _lib.ptr(scale),
                                                _lib.ptr(shift), 1 if relu else 0, _lib.ptr(stats), 0, passes,
                                                _lib.stream_ptr()), "selavi_conv_gemm(fwd)")
@@ -243,7 +250,7 @@ def conv_dgrad(dz, wpack_t, geom, out=None, accumulate=False, passes=3):
         out = torch.empty(geom.in_shape(), dtype=torch.float32, device=dz.device)
         accumulate = False
     _chk(out, geom.in_shape(), "dx")
-    with _Guard(dz.device), _Prof("conv_dgrad", geom):
+    with _Guard(dz.device), _Prof("conv_dgrad", geom, "conv_igemm_kernel[dgrad tf32x3]"):
         _lib.check(_lib.lib().selavi_conv_gemm(_lib.ptr(dz), _lib.ptr(out), _lib.ptr(wpack_t), geom.arr(1), None, None, 0,
                                                None, 1 if accumulate else 0, passes, _lib.stream_ptr()),
                    "selavi_conv_gemm(dgrad)")
@@ -266,7 +273,7 @@ def conv_wgrad(x, dz, geom, dw, scale=None, shift=None, relu=False, accumulate=F
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         _wgrad_ws[key] = ws
-    with _Guard(x.device), _Prof("conv_wgrad", geom):
+    with _Guard(x.device), _Prof("conv_wgrad", geom, "wgrad_kernel[tf32x3]"):
         _lib.check(lib.selavi_conv_wgrad(_lib.ptr(x), _lib.ptr(dz), _lib.ptr(dw), geom.arr(0), geom.ci, _lib.ptr(scale),
                                          _lib.ptr(shift), 1 if relu else 0, _lib.ptr(ws), 1 if accumulate else 0, passes,
                                          _lib.stream_ptr()), "selavi_conv_wgrad")
@@ -316,7 +323,7 @@ def conv_dgrad_bf16(z_hi, z_lo, wpack_bf16, geom, out=None, accumulate=False, pa
         out = torch.empty(geom.in_shape(), dtype=torch.float32, device=z_hi.device)
         accumulate = False
     _chk(out, geom.in_shape(), "dx")
-    with _Guard(z_hi.device), _Prof("conv_dgrad", geom):
+    with _Guard(z_hi.device), _Prof("conv_dgrad", geom, "dgrad_bf16_kernel"):
         _lib.check(_lib.lib().selavi_conv_dgrad_bf16(_lib.ptr(z_hi), _lib.ptr(z_lo), _lib.ptr(out), _lib.ptr(wpack_bf16),
                                                      geom.arr(1), 1 if accumulate else 0, passes, _lib.stream_ptr()),
                    "selavi_conv_dgrad_bf16")
@@ -336,7 +343,7 @@ def conv_wgrad_bf16(x, z_hi, z_lo, geom, dw, scale=None, shift=None, relu=False,
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         _wgrad_ws[key] = ws
-    with _Guard(x.device), _Prof("conv_wgrad", geom):
+    with _Guard(x.device), _Prof("conv_wgrad", geom, "wgrad_bf16_kernel(+split,reduce)"):
         _lib.check(lib.selavi_conv_wgrad_bf16(_lib.ptr(x), _lib.ptr(z_hi), _lib.ptr(z_lo), _lib.ptr(dw), geom.arr(0), geom.ci,
                                               _lib.ptr(scale), _lib.ptr(shift), 1 if relu else 0, _lib.ptr(ws),
                                               1 if accumulate else 0, passes, _lib.stream_ptr()), "selavi_conv_wgrad_bf16")
