@@ -182,6 +182,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
                 }
             }
         };
+        // 16-byte column c of chunk kc is read by the MMAs only when it lies inside the chunk's valid k16 steps
+        auto col_used = [&](int kc) { return c * 8 < ((p.cs - kc * 64 + 15) & ~15); };
         auto gather = [&](HlBatch& b, const int jbase, int kc) {
             const int ch = kc * 64 + c * 8;
             const bool chan_ok = ch < p.cs;
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
             }
         };
         auto commit = [&](const HlBatch& b, const int jbase, int kc, uint32_t a_hi) {
+            if (!col_used(kc)) return;
             const uint32_t a_lo = a_hi + (uint32_t)a_plane;
             const int ch = kc * 64 + c * 8;
             const float4 sc0 = *reinterpret_cast<const float4*>(s_pro + ch);
@@ -254,9 +257,10 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
                 const uint32_t a_lo = a_hi + (uint32_t)a_plane;
                 const int ch = kc * 64 + c * 8;
                 const bool chan_ok = ch < p.cs;
+                const bool used = col_used(kc);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    if (j < nrow_thr) {
+                    if (j < nrow_thr && used) {
                         const bool ok = chan_ok && pb[j] >= 0;
                         const size_t goff = ok ? (size_t)pb[j] * p.cs + ch : 0;
                         const uint32_t nbytes = ok ? 16u : 0u;
@@ -481,7 +485,47 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
         if (lane == 0) {
             int sb = 0;
             uint32_t pbp = 0;
+            const size_t px_bytes = p.src_kind == 1 ? (size_t)p.cs * 2 : (size_t)p.cs * 4;
+            auto prefetch_range = [&](size_t pix0, int npix) {   // [pix0, pix0+npix) of the source tensor(s) -> L2
+                size_t off = pix0 * px_bytes, left = (size_t)npix * px_bytes;
+                while (left > 0) {
+                    const uint32_t n = left > 32768 ? 32768u : (uint32_t)left;
+                    if (p.src_kind == 1) {
+                        sv::bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(p.src_hi) + off, n);
+                        sv::bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(p.src_lo) + off, n);
+                    } else {
+                        sv::bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(p.src) + off, n);
+                    }
+                    off += n;
+                    left -= n;
+                }
+            };
+            // the input window of a tile is a few contiguous pixel ranges: pull the NEXT tile's window into L2 while
+            // this one is processed, so that the loaders' gathers see L2 rather than DRAM latency
+            auto prefetch_tile = [&](int tile) {
+                const int m_tile = tile / p.ntiles;
+                if (p.mode == 0) {
+                    const int sb = m_tile % p.SB;
+                    const int t1 = m_tile / p.SB;
+                    const int tb = t1 % p.TB;
+                    const int n = t1 / p.TB;
+                    const int s0 = sb * 16;
+                    const int ns = p.S - s0 < 16 ? p.S - s0 : 16;
+                    for (int t = tb * 8 - 1; t <= tb * 8 + 8; ++t)
+                        if (t >= 0 && t < p.T) prefetch_range((size_t)(n * p.T + t) * p.S + s0, ns);
+                } else {
+                    const int ob = m_tile % p.OB;
+                    const int f = m_tile / p.OB;
+                    int h0 = (ob * 128) / p.WP - 1, h1 = (ob * 128 + p.rows - 1) / p.WP - 1;
+                    if (h0 < 0) h0 = 0;
+                    if (h1 > p.H - 1) h1 = p.H - 1;
+                    if (h1 >= h0) prefetch_range((size_t)(f * p.H + h0) * p.W, (h1 - h0 + 1) * p.W);
+                }
+            };
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                // (measured: +7 % on the register-staged fp32 loaders, slightly negative on the cp.async-fed bf16 planes)
+                if (p.src_kind == 0 && tile + (int)gridDim.x < total_tiles && (p.ntiles == 1 || tile % p.ntiles == 0))
+                    prefetch_tile(tile + gridDim.x);
                 const int ntile = tile % p.ntiles;
                 const unsigned char* wsrc = p.wpack + (size_t)ntile * p.kchunks * p.taps * b_slot_bytes;
                 const int nslots = p.kchunks * p.taps;

@@ -37,6 +37,20 @@ def _world(bn):
     return 1
 
 
+# weight gradients are off the critical path of backward (nothing downstream reads dW before the optimizer): launch them
+# on a side stream so that they overlap the HBM-bound BatchNorm-backward passes and the data gradient of the layers below
+WGRAD_STREAM = os.environ.get("SELAVI_WGRAD_STREAM", "1") == "1"
+_side_streams = {}
+
+
+def _side_stream(dev):
+    s = _side_streams.get(dev.index)
+    if s is None:
+        s = torch.cuda.Stream(device=dev)
+        _side_streams[dev.index] = s
+    return s
+
+
 # cross-rank exchange of the SyncBN statistic vectors: "p2p" = one tiny kernel over NVSwitch peer memory (default inside
 # one node, world <= 8), "nccl" = torch.distributed.all_reduce
 BN_EXCHANGE = os.environ.get("SELAVI_BN_EXCHANGE", "p2p")
@@ -290,7 +304,17 @@ class TowerRunner:
                                            _lib.ptr(z_hi), _lib.ptr(z_lo), _stream()), "selavi_bn_bwd_apply")
         if need_dw:
             dw = torch.empty_like(conv.weight)
-            if bf16:
+            if bf16 and WGRAD_STREAM:
+                main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    ops.conv_wgrad_bf16(inp.t, z_hi, z_lo, geom, dw, scale=inp.scale, shift=inp.shift, relu=inp.relu,
+                                        passes=3 if PASSES == 3 else 1)
+                for t in (inp.t, z_hi, z_lo, dw, inp.scale, inp.shift):
+                    if t is not None:
+                        t.record_stream(side)
+                self._side_busy = True
+            elif bf16:
                 ops.conv_wgrad_bf16(inp.t, z_hi, z_lo, geom, dw, scale=inp.scale, shift=inp.shift, relu=inp.relu,
                                     passes=3 if PASSES == 3 else 1)
             else:
@@ -310,6 +334,14 @@ class TowerRunner:
         return ops.conv_dgrad(dz, wpt, geom, out=dx_out, accumulate=dx_accumulate, passes=PASSES)
 
     def backward(self, tape, dfeat, grads):
+        self._side_busy = False
+        try:
+            self._backward(tape, dfeat, grads)
+        finally:
+            if self._side_busy:   # the weight gradients must be complete before autograd hands them to DDP / the optimizer
+                torch.cuda.current_stream(dfeat.device).wait_stream(_side_stream(dfeat.device))
+
+    def _backward(self, tape, dfeat, grads):
         lib = _lib.lib()
         dfeat = dfeat.contiguous()
         g = None

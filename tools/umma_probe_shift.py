@@ -116,6 +116,8 @@ if __name__ == "__main__":
         for i, c in enumerate(CASES):     # wrong layouts only give wrong numbers: safe in one process
             if c[0] == "shift":
                 main(i)
+    elif len(sys.argv) > 1 and sys.argv[1] == "mn":
+        pass
     elif len(sys.argv) > 1:
         main(int(sys.argv[1]))
     else:
@@ -129,3 +131,32 @@ if __name__ == "__main__":
                 print(f"[{i}] rc={r.returncode} " + (" | ".join(out[-2:]) if out else "(no output)"), flush=True)
             except subprocess.TimeoutExpired:
                 print(f"[{i}] TIMEOUT", flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# 3. MN-major A operand built from two row-shifted windows of one linear [k (pixel)][64 mn (channel)] array: the
+#    weight-gradient GEMM with tap reuse.  M = 128 = window(q_a) | window(q_b); LBO = (q_b - q_a) * 128 bytes.
+def case_mn_pair(qa, qb, dev):
+    rng = np.random.default_rng(3)
+    N, nk = 64, 2
+    K = 16 * nk
+    X = rounded(rng.standard_normal((256, 64)).astype(np.float32), 1)      # [pixel row][channel]
+    B = rounded(rng.standard_normal((N, K)).astype(np.float32), 1)
+    A = np.concatenate([X[qa:qa + K].T, X[qb:qb + K].T], 0)                # [128 (window, channel)][K pixels]
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    a_img = img_rows_sw128(X, 1)            # row r at r*128, 16B chunk c at c ^ (r & 7): the MN-major SW128 atom layout
+    b_img = img_rows_sw128(B, 1)
+    offs_a = [(qa + 16 * k) * 128 for k in range(nk)]
+    offs_b = [k * 32 for k in range(nk)]
+    lbo = (qb - qa) * 128
+    idesc = (1 << 4) | (1 << 7) | (1 << 10) | (1 << 15) | (0 << 16) | ((N >> 3) << 17) | ((128 >> 4) << 24)
+    out = run(a_img, offs_a, desc_bits(lbo, 1024, 2), b_img, offs_b, desc_bits(16, 1024, 2), idesc, N, dev)
+    err = np.linalg.norm(out - ref) / np.linalg.norm(ref)
+    e0 = np.linalg.norm(out[:64] - ref[:64]) / np.linalg.norm(ref[:64])
+    e1 = np.linalg.norm(out[64:] - ref[64:]) / np.linalg.norm(ref[64:])
+    print(f"mn_pair qa={qa:3d} qb={qb:3d} lbo={lbo:6d} rel={err:.3e} (rows 0-63 {e0:.2e}, rows 64-127 {e1:.2e})", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "mn":
+    for qa, qb in ((0, 8), (0, 64), (0, 1), (3, 4), (3, 61), (5, 63), (17, 133), (9, 9)):
+        case_mn_pair(qa, qb, torch.device("cuda:0"))
