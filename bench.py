@@ -200,20 +200,41 @@ def run_ours(args):
     host_ms = (time.perf_counter() - t0) * 1e3
     torch.cuda.synchronize()
 
-    def e2e_step():
-        v = video_h.to(dev, non_blocking=True)
-        s = spec_h.to(dev, non_blocking=True)
-        lab = labels_h.to(dev, non_blocking=True)
-        return float(train_step(v, s, lab).item())
+    # end to end through the public API from pinned host buffers: every step copies ITS batch host->device (on a copy
+    # stream, issued while the previous step computes, as a prefetching data loader would) and reads the loss back
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [[torch.empty_like(video_d), torch.empty_like(spec_d), torch.empty_like(labels_d), torch.cuda.Event()] for _ in range(2)]
+    state = {"k": 0}
 
+    def h2d(slot):
+        copy_stream.wait_stream(torch.cuda.current_stream(dev))     # the slot's previous consumer has been enqueued
+        with torch.cuda.stream(copy_stream):
+            slot[0].copy_(video_h, non_blocking=True)
+            slot[1].copy_(spec_h, non_blocking=True)
+            slot[2].copy_(labels_h, non_blocking=True)
+            slot[3].record(copy_stream)
+
+    def e2e_step():
+        cur = slots[state["k"] & 1]
+        nxt = slots[(state["k"] + 1) & 1]
+        state["k"] += 1
+        torch.cuda.current_stream(dev).wait_event(cur[3])
+        loss = train_step(cur[0], cur[1], cur[2])
+        h2d(nxt)                                                      # next step's batch: overlaps this step's kernels
+        return float(loss.item())
+
+    h2d(slots[0])
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if sampler else None
 
     # ---- live per-kernel timing of one more step (CUDA events around every conv launch on the launching stream)
+    from selavi_b200 import engine
     ops.PROFILE = []
+    side, engine.WGRAD_STREAM = engine.WGRAD_STREAM, False   # per-kernel times: no concurrent weight-gradient stream
     train_step(video_d, spec_d, labels_d)
     torch.cuda.synchronize()
+    engine.WGRAD_STREAM = side
     prof, ops.PROFILE = ops.PROFILE, None
     agg = {}
     if os.environ.get("SELAVI_BENCH_DETAIL") and rank == 0:
@@ -226,7 +247,6 @@ def run_ours(args):
         a[1] += e0.elapsed_time(e1)
         a[2] += 1
     ms_step = ms_total / args.steps
-    from selavi_b200 import engine
     # per kernel: algorithmic conv FLOPs (2*M*Co*Ci*taps) / launch time, CUDA events on the launching
     # stream.  The x3 operand split issues 3 MMAs per algorithmic MAC, so `issued_mma_tflops` = 3x achieved; the fp16x3 /
     # bf16x3 kernels run at the bf16 rate (ceiling 1/3 of the peak below), the tf32x3 kernels at half of it (ceiling 1/6).

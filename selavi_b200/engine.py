@@ -46,7 +46,7 @@ _side_streams = {}
 def _side_stream(dev):
     s = _side_streams.get(dev.index)
     if s is None:
-        s = torch.cuda.Stream(device=dev)
+        s = torch.cuda.Stream(device=dev, priority=int(os.environ.get("SELAVI_WGRAD_PRIORITY", "-1")))
         _side_streams[dev.index] = s
     return s
 
