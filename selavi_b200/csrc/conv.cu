@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
     int* tap_dt = reinterpret_cast<int*>(tmem_slot + 2);            // [MAX_TAPS] packed (kt | kh<<8 | kw<<16)
     int* tap_off = tap_dt + MAX_TAPS;                               // [MAX_TAPS] pixel offset of the tap
     float* s_stat = reinterpret_cast<float*>(tap_off + MAX_TAPS);   // [EPI_WARPS][2][256]
+    unsigned char* s_stage = reinterpret_cast<unsigned char*>(         // [EPI_WARPS] x (32 rows x 128 B | 32 row indices)
+        (reinterpret_cast<uintptr_t>(s_stat + EPI_WARPS * 512) + 127) & ~(uintptr_t)127);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int taps = p.kt * p.kh * p.kw;
@@ -279,9 +281,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
     } else if (warp < EPI_WARPS) {
         // ------------------------------------------------------------------ epilogue (4 warps, one TMEM quadrant each)
         const int quad = warp;
-        const int units = p.bnt >> 4;  // 16-column units
         const int ctot = p.ntiles * p.bnt;
         float* my_stat = s_stat + (size_t)warp * 512;
+        unsigned char* my_stage = s_stage + (size_t)warp * sv::EPI_STAGE_BYTES;
+        const uint32_t stg = sv::smem_u32(my_stage);
+        int* row_pix = reinterpret_cast<int*>(my_stage + 32 * 128);
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -289,66 +293,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
             const int m = m_tile * BM + quad * 32 + lane;
             const bool row_ok = m < p.M;
             const int n_base = ntile * p.bnt;
-            float* out_row = p.dst + (size_t)(row_ok ? m : 0) * p.cd;
+            row_pix[lane] = row_ok ? m : -1;
+            __syncwarp();
             sv::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
             sv::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * (p.tmem_cols >> 1);
-            for (int u = 0; u < units; ++u) {
-                uint32_t av[16];
-                sv::tmem_ld16(taddr + (uint32_t)(u * 16), av);
-                sv::tmem_ld_wait();
-                float f[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(av[i]);
-                const int ncol = n_base + u * 16;
-                if (row_ok) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        if (ncol + i < p.cd) {
-                            float4* dp = reinterpret_cast<float4*>(out_row + ncol + i);
-                            float4 o = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                            if (p.accumulate) {
-                                const float4 old = *dp;
-                                o.x += old.x;
-                                o.y += old.y;
-                                o.z += old.z;
-                                o.w += old.w;
-                            }
-                            *dp = o;
-                        }
-                    }
-                }
-                if (p.stats != nullptr) {
-                    // column sums over this warp's 32 rows (rows past M hold exact zeros): transpose-reduce
-                    float s1[16], s2[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        s1[i] = f[i];
-                        s2[i] = f[i] * f[i];
-                    }
-#pragma unroll
-                    for (int off = 16, n = 8; off >= 2; off >>= 1, n >>= 1) {
-                        const bool upper = (lane & off) != 0;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (i < n) {
-                                const float send1 = upper ? s1[i] : s1[i + n];
-                                const float keep1 = upper ? s1[i + n] : s1[i];
-                                s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
-                                const float send2 = upper ? s2[i] : s2[i + n];
-                                const float keep2 = upper ? s2[i + n] : s2[i];
-                                s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
-                            }
-                        }
-                    }
-                    s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
-                    s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
-                    if ((lane & 1) == 0) {  // lane L holds column (L >> 1) of this unit
-                        my_stat[u * 16 + (lane >> 1)] = s1[0];
-                        my_stat[256 + u * 16 + (lane >> 1)] = s2[0];
-                    }
-                }
-            }
+            // coalesced drain through the per-warp staging tile (+ the BN column sums), see sv::epi_drain_group
+            sv::epi_drain_tile(taddr, p.bnt, 1.f, row_ok, stg, row_pix, p.dst, p.cd, n_base, p.accumulate, true,
+                               p.stats != nullptr ? my_stat : nullptr, lane);
             // accumulator drained: hand the TMEM buffer back to the MMA warp
             sv::tc_fence_before();
             __syncwarp();
@@ -366,44 +318,52 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
             }
         }
     } else if (warp == MMA_WARP) {
-        // ------------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer
+        // the warp stays converged (warp-uniform schedule => descriptors in uniform registers), one elected lane issues;
+        // a divergent `if (lane == 0)` makes the compiler wrap each tcgen05.mma in an elect/broadcast/branch loop
+        {
             const uint32_t idesc = sv::make_idesc_tf32(BM, p.bnt, 0, 0);
+            const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint64_t desc_fixed = sv::make_smem_desc_sw128(0, 16, 1024);
             int stage = 0, it = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
                 sv::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
                 sv::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * (p.tmem_cols >> 1);
+                const uint32_t d_tmem = tm0 + (uint32_t)acc * (p.tmem_cols >> 1);
                 for (int ks = 0; ks < p.kstages; ++ks) {
                     sv::mbar_wait(&full_bar[stage], phase);
                     sv::tc_fence_after();
                     const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t a_lo = a_hi + A_TILE_BYTES;
-                    const uint32_t b_hi = a_lo + A_TILE_BYTES;
-                    const uint32_t b_lo = b_hi + b_tile_bytes;
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        const uint64_t da_hi = sv::make_smem_desc_sw128(a_hi + k4 * 32, 16, 1024);
-                        const uint64_t db_hi = sv::make_smem_desc_sw128(b_hi + k4 * 32, 16, 1024);
+                    // k-step k4 adds 32 bytes = 2 to the descriptor's 16-byte-unit address field
+                    const uint64_t da_hi = desc_fixed | (uint64_t)((a_hi & 0x3FFFFu) >> 4);
+                    const uint64_t da_lo = da_hi + (uint64_t)(A_TILE_BYTES >> 4);
+                    const uint64_t db_hi = da_lo + (uint64_t)(A_TILE_BYTES >> 4);
+                    const uint64_t db_lo = db_hi + (uint64_t)(b_tile_bytes >> 4);
+                    if (sv::elect_one()) {
                         if (p.passes == 3) {
-                            const uint64_t da_lo = sv::make_smem_desc_sw128(a_lo + k4 * 32, 16, 1024);
-                            const uint64_t db_lo = sv::make_smem_desc_sw128(b_lo + k4 * 32, 16, 1024);
-                            sv::umma_tf32(d_tmem, da_lo, db_hi, idesc, (ks | k4) ? 1u : 0u);
-                            sv::umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
-                            sv::umma_tf32(d_tmem, da_hi, db_hi, idesc, 1u);
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                sv::umma_tf32(d_tmem, da_lo + 2 * k4, db_hi + 2 * k4, idesc, (uint32_t)(ks | k4));
+                                sv::umma_tf32(d_tmem, da_hi + 2 * k4, db_lo + 2 * k4, idesc, 1u);
+                                sv::umma_tf32(d_tmem, da_hi + 2 * k4, db_hi + 2 * k4, idesc, 1u);
+                            }
                         } else {
-                            sv::umma_tf32(d_tmem, da_hi, db_hi, idesc, (ks | k4) ? 1u : 0u);
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                sv::umma_tf32(d_tmem, da_hi + 2 * k4, db_hi + 2 * k4, idesc, (uint32_t)(ks | k4));
                         }
+                        sv::umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
                     }
-                    sv::umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+                    __syncwarp();
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                sv::umma_commit(&tfull_bar[acc]);  // accumulator complete
+                if (sv::elect_one()) sv::umma_commit(&tfull_bar[acc]);  // accumulator complete
+                __syncwarp();
             }
         }
     } else {
@@ -546,7 +506,7 @@ extern "C" int selavi_conv_gemm(const float* src, float* dst, const void* wpack,
     while ((int)cols < 2 * p.bnt) cols <<= 1;  // two accumulators (epilogue of tile i overlaps the MMAs of tile i+1)
     p.tmem_cols = cols;
     const int stage_bytes = 2 * A_TILE_BYTES + 2 * p.bnt * 128;
-    const int tail_bytes = (2 * MAX_STAGES + 4) * 8 + 8 + 2 * MAX_TAPS * 4 + EPI_WARPS * 512 * 4 + 64;
+    const int tail_bytes = (2 * MAX_STAGES + 4) * 8 + 8 + 2 * MAX_TAPS * 4 + EPI_WARPS * 512 * 4 + EPI_WARPS * sv::EPI_STAGE_BYTES + 128 + 64;
     int stages = (227 * 1024 - 1024 - tail_bytes) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages > p.kstages) stages = p.kstages < 1 ? 1 : p.kstages;

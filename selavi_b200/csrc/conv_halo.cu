@@ -34,7 +34,7 @@ constexpr int HL_MMA_WARP = HL_EPI_WARPS + HL_LOADER_WARPS;
 constexpr int HL_BPROD_WARP = HL_MMA_WARP + 1;
 constexpr int HL_THREADS = (HL_BPROD_WARP + 1) * 32;
 constexpr int HL_MAX_A = 3;
-constexpr int HL_MAX_B = 8;
+constexpr int HL_MAX_B = 16;
 constexpr float HL_ASCALE = 16.f;
 constexpr float HL_WSCALE = 256.f;
 constexpr float HL_OSCALE = 1.f / (16.f * 256.f);
@@ -58,6 +58,8 @@ struct HaloParams {
     int n_a, n_b;
     int pro_relu, use_base_off;
     int src_kind, accumulate;
+    int b_split;                 // 1: hi and lo weight planes travel in separate pipeline slots (finer B pipeline)
+    int dbg;                     // timing diagnostics only (results invalid): 2 no B reloads, 4 no A gathers, 8 no stores
     float oscale;
     uint32_t tmem_cols;
 };
@@ -74,13 +76,6 @@ __device__ __forceinline__ void hl_named_bar_sync(int id, int nthreads) {
 }
 __device__ __forceinline__ uint32_t hl_h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
-// K-major SWIZZLE_128B descriptor of a window that starts at an arbitrary 128-byte row of a linear row array
-__device__ __forceinline__ uint64_t hl_desc(uint32_t saddr, int use_base_off) {
-    uint64_t d = sv::make_smem_desc_sw128(saddr, 16, 1024);
-    if (use_base_off) d |= static_cast<uint64_t>((saddr >> 7) & 7u) << 49;
-    return d;
-}
-
 struct HlBatch {
     float4 v[4][2];
     uint32_t ok;
@@ -92,7 +87,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
     const int a_plane = p.rows_alloc * 128;
     const int a_slot_bytes = 2 * a_plane;
     const int b_plane = p.bnt * 128;
-    const int b_slot_bytes = 2 * b_plane;
+    const int b_slot_bytes = p.b_split ? b_plane : 2 * b_plane;
     unsigned char* a_base = smem;
     unsigned char* b_base = a_base + (size_t)p.n_a * a_slot_bytes;
     unsigned char* tail = b_base + (size_t)p.n_b * b_slot_bytes;
@@ -105,6 +100,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);   // [EPI_WARPS][2][256]
     float* s_pro = s_stat + HL_EPI_WARPS * 512;                 // [2][kchunks*64]: scale*16 | shift*16
+    unsigned char* s_stage = reinterpret_cast<unsigned char*>(     // [EPI_WARPS] x (32 rows x 128 B | 32 row indices)
+        (reinterpret_cast<uintptr_t>(s_pro + 2 * p.kchunks * 64) + 127) & ~(uintptr_t)127);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int total_tiles = p.m_tiles * p.ntiles;
@@ -260,7 +257,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
                 const bool used = col_used(kc);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    if (j < nrow_thr && used) {
+                    if (j < nrow_thr && used && !(p.dbg & 4)) {
                         const bool ok = chan_ok && pb[j] >= 0;
                         const size_t goff = ok ? (size_t)pb[j] * p.cs + ch : 0;
                         const uint32_t nbytes = ok ? 16u : 0u;
@@ -292,16 +289,17 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
             if (lane == 0 && prev_slot >= 0) sv::mbar_arrive(&a_full[prev_slot]);
         }
         HlBatch sa, sb;
+        const bool no_a = (p.dbg & 4) != 0;
         if (p.src_kind == 1) tile = total_tiles;
         if (tile < total_tiles) {
             setup(tile);
-            gather(sa, 0, 0);
+            if (!no_a) gather(sa, 0, 0);
         }
         while (tile < total_tiles) {
-            gather(sb, 4, kc);   // rows 4..7 of this slot in flight while rows 0..3 are converted
+            if (!no_a) gather(sb, 4, kc);   // rows 4..7 of this slot in flight while rows 0..3 are converted
             sv::mbar_wait(&a_empty[slot], phase ^ 1);
             const uint32_t a_hi = sv::smem_u32(a_base + (size_t)slot * a_slot_bytes);
-            commit(sa, 0, kc, a_hi);
+            if (!no_a) commit(sa, 0, kc, a_hi);
             int ntile = tile, nkc = kc + 1;
             if (nkc == p.kchunks) {
                 nkc = 0;
@@ -309,9 +307,9 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
             }
             if (ntile < total_tiles) {
                 if (ntile != tile) setup(ntile);
-                gather(sa, 0, nkc);   // first rows of the NEXT slot in flight while rows 4..7 are converted
+                if (!no_a) gather(sa, 0, nkc);   // first rows of the NEXT slot in flight while rows 4..7 are converted
             }
-            commit(sb, 4, kc, a_hi);
+            if (!no_a) commit(sb, 4, kc, a_hi);
             sv::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) sv::mbar_arrive(&a_full[slot]);
@@ -325,9 +323,11 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
     } else if (warp < HL_EPI_WARPS) {
         // ------------------------------------------------------------------ epilogue (4 warps, one TMEM quadrant each)
         const int quad = warp;
-        const int units = p.bnt >> 4;
         const int ctot = p.ntiles * p.bnt;
         float* my_stat = s_stat + (size_t)warp * 512;
+        unsigned char* my_stage = s_stage + (size_t)warp * sv::EPI_STAGE_BYTES;
+        const uint32_t stg = sv::smem_u32(my_stage);
+        int* row_pix = reinterpret_cast<int*>(my_stage + 32 * 128);
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -352,67 +352,14 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
                 row_ok = (h < p.H) & (w < p.W);
                 pix = (f * p.H + h) * p.W + w;
             }
+            row_pix[lane] = row_ok ? pix : -1;
+            __syncwarp();
             const int n_base = ntile * p.bnt;
-            float* out_row = p.dst + (size_t)(row_ok ? pix : 0) * p.cd;
             sv::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
             sv::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * (p.tmem_cols >> 1);
-            for (int u = 0; u < units; ++u) {
-                uint32_t av[16];
-                sv::tmem_ld16(taddr + (uint32_t)(u * 16), av);
-                sv::tmem_ld_wait();
-                float f[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = row_ok ? __uint_as_float(av[i]) * p.oscale : 0.f;
-                const int ncol = n_base + u * 16;
-                if (row_ok) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        if (ncol + i < p.cd) {
-                            float4* dp = reinterpret_cast<float4*>(out_row + ncol + i);
-                            float4 o = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                            if (p.accumulate) {
-                                const float4 old = *dp;
-                                o.x += old.x;
-                                o.y += old.y;
-                                o.z += old.z;
-                                o.w += old.w;
-                            }
-                            *dp = o;
-                        }
-                    }
-                }
-                if (p.stats != nullptr) {
-                    // column sums over this warp's 32 rows (masked rows are exact zeros): transpose-reduce
-                    float s1[16], s2[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        s1[i] = f[i];
-                        s2[i] = f[i] * f[i];
-                    }
-#pragma unroll
-                    for (int off = 16, n = 8; off >= 2; off >>= 1, n >>= 1) {
-                        const bool upper = (lane & off) != 0;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (i < n) {
-                                const float send1 = upper ? s1[i] : s1[i + n];
-                                const float keep1 = upper ? s1[i + n] : s1[i];
-                                s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
-                                const float send2 = upper ? s2[i] : s2[i + n];
-                                const float keep2 = upper ? s2[i + n] : s2[i];
-                                s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
-                            }
-                        }
-                    }
-                    s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
-                    s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
-                    if ((lane & 1) == 0) {  // lane L holds column (L >> 1) of this unit
-                        my_stat[u * 16 + (lane >> 1)] = s1[0];
-                        my_stat[256 + u * 16 + (lane >> 1)] = s2[0];
-                    }
-                }
-            }
+            sv::epi_drain_tile(taddr, p.bnt, p.oscale, row_ok, stg, row_pix, p.dst, p.cd, n_base, p.accumulate, !(p.dbg & 8),
+                               p.stats != nullptr ? my_stat : nullptr, lane);
             sv::tc_fence_before();
             __syncwarp();
             if (lane == 0) sv::mbar_arrive(&tempty_bar[acc]);
@@ -429,55 +376,99 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
             }
         }
     } else if (warp == HL_MMA_WARP) {
-        // ------------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer
+        // The whole warp walks the schedule converged (all values warp-uniform, so descriptors live in uniform
+        // registers) and one elected lane issues: under a divergent `if (lane == 0)` the compiler has to wrap every
+        // tcgen05.mma in an elect / register-broadcast / branch loop, which made the ISSUE the bottleneck (~180 clk per
+        // MMA on every layer, profiles/r01i_halo_diag.txt).
+        {
             const int fmt = p.src_kind == 1 ? 1 : 0;   // fp16 x fp16 (forward) or bf16 x bf16 (data gradient), K-major
             const uint32_t idesc = sv::make_idesc_f16(128, p.bnt, fmt, fmt, 0, 0);
+            const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint64_t desc_fixed = sv::make_smem_desc_sw128(0, 16, 1024);
             int sa = 0, sb = 0, it = 0;
             uint32_t pa = 0, pbp = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
                 sv::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
                 sv::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * (p.tmem_cols >> 1);
-                uint32_t first = 0;
+                const uint32_t d_tmem = tm0 + (uint32_t)acc * (p.tmem_cols >> 1);
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     int nk16 = (p.cs - kc * 64 + 15) >> 4;
                     if (nk16 > 4) nk16 = 4;
                     sv::mbar_wait(&a_full[sa], pa);
                     sv::tc_fence_after();
                     const uint32_t a_hi = sv::smem_u32(a_base + (size_t)sa * a_slot_bytes);
-                    const uint32_t a_lo = a_hi + (uint32_t)a_plane;
                     for (int tap = 0; tap < p.taps; ++tap) {
                         const int shift_rows = p.mode == 0 ? tap * 16 : (tap / 3) * p.WP + (tap % 3);
-                        const uint32_t sh = (uint32_t)shift_rows * 128u;
+                        const uint32_t a_tap = a_hi + (uint32_t)shift_rows * 128u;
+                        const uint32_t started = (uint32_t)(kc | tap);   // 0 only for the opening MMA group of a tile
+                        // descriptors of k16 step 0; step k adds 32 bytes = 2 to the 16-byte-unit address field
+                        uint64_t da_hi = desc_fixed | (uint64_t)((a_tap & 0x3FFFFu) >> 4);
+                        if (p.use_base_off) da_hi |= (uint64_t)((a_tap >> 7) & 7u) << 49;
+                        const uint64_t da_lo = da_hi + (uint64_t)(a_plane >> 4);
                         sv::mbar_wait(&b_full[sb], pbp);
                         sv::tc_fence_after();
                         const uint32_t b_hi = sv::smem_u32(b_base + (size_t)sb * b_slot_bytes);
-                        const uint32_t b_lo = b_hi + (uint32_t)b_plane;
-                        for (int k = 0; k < nk16; ++k) {
-                            const uint64_t da_hi = hl_desc(a_hi + sh + k * 32, p.use_base_off);
-                            const uint64_t da_lo = hl_desc(a_lo + sh + k * 32, p.use_base_off);
-                            const uint64_t db_hi = sv::make_smem_desc_sw128(b_hi + k * 32, 16, 1024);
-                            const uint64_t db_lo = sv::make_smem_desc_sw128(b_lo + k * 32, 16, 1024);
-                            sv::umma_f16(d_tmem, da_lo, db_hi, idesc, first);
-                            sv::umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
-                            sv::umma_f16(d_tmem, da_hi, db_hi, idesc, 1u);
-                            first = 1u;
+                        const uint64_t db_hi = desc_fixed | (uint64_t)((b_hi & 0x3FFFFu) >> 4);
+                        if (p.b_split) {
+                            // hi plane: the two products that read it; then the lo plane from the next slot
+                            if (sv::elect_one()) {
+                                for (int k = 0; k < nk16; ++k) {
+                                    sv::umma_f16(d_tmem, da_lo + 2 * k, db_hi + 2 * k, idesc, started | (uint32_t)k);
+                                    sv::umma_f16(d_tmem, da_hi + 2 * k, db_hi + 2 * k, idesc, 1u);
+                                }
+                                sv::umma_commit(&b_empty[sb]);
+                            }
+                            __syncwarp();
+                            if (++sb == p.n_b) {
+                                sb = 0;
+                                pbp ^= 1;
+                            }
+                            sv::mbar_wait(&b_full[sb], pbp);
+                            sv::tc_fence_after();
+                            const uint32_t b_lo = sv::smem_u32(b_base + (size_t)sb * b_slot_bytes);
+                            const uint64_t db_lo = desc_fixed | (uint64_t)((b_lo & 0x3FFFFu) >> 4);
+                            if (sv::elect_one()) {
+                                for (int k = 0; k < nk16; ++k) sv::umma_f16(d_tmem, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
+                                sv::umma_commit(&b_empty[sb]);
+                            }
+                            __syncwarp();
+                        } else {
+                            const uint64_t db_lo = db_hi + (uint64_t)(b_plane >> 4);
+                            if (sv::elect_one()) {
+                                if (nk16 == 4) {   // full 64-channel chunk: 12 MMAs back to back, descriptor offsets folded
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        sv::umma_f16(d_tmem, da_lo + 2 * k, db_hi + 2 * k, idesc, started | (uint32_t)k);
+                                        sv::umma_f16(d_tmem, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
+                                        sv::umma_f16(d_tmem, da_hi + 2 * k, db_hi + 2 * k, idesc, 1u);
+                                    }
+                                } else {
+                                    for (int k = 0; k < nk16; ++k) {
+                                        sv::umma_f16(d_tmem, da_lo + 2 * k, db_hi + 2 * k, idesc, started | (uint32_t)k);
+                                        sv::umma_f16(d_tmem, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
+                                        sv::umma_f16(d_tmem, da_hi + 2 * k, db_hi + 2 * k, idesc, 1u);
+                                    }
+                                }
+                                sv::umma_commit(&b_empty[sb]);
+                            }
+                            __syncwarp();
                         }
-                        sv::umma_commit(&b_empty[sb]);
                         if (++sb == p.n_b) {
                             sb = 0;
                             pbp ^= 1;
                         }
                     }
-                    sv::umma_commit(&a_empty[sa]);
+                    if (sv::elect_one()) sv::umma_commit(&a_empty[sa]);
+                    __syncwarp();
                     if (++sa == p.n_a) {
                         sa = 0;
                         pa ^= 1;
                     }
                 }
-                sv::umma_commit(&tfull_bar[acc]);
+                if (sv::elect_one()) sv::umma_commit(&tfull_bar[acc]);
+                __syncwarp();
             }
         }
     } else {
@@ -527,13 +518,17 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
                 if (p.src_kind == 0 && tile + (int)gridDim.x < total_tiles && (p.ntiles == 1 || tile % p.ntiles == 0))
                     prefetch_tile(tile + gridDim.x);
                 const int ntile = tile % p.ntiles;
-                const unsigned char* wsrc = p.wpack + (size_t)ntile * p.kchunks * p.taps * b_slot_bytes;
-                const int nslots = p.kchunks * p.taps;
+                const int nslots = p.kchunks * p.taps * (p.b_split ? 2 : 1);
+                const unsigned char* wsrc = p.wpack + (size_t)ntile * nslots * b_slot_bytes;
                 for (int i = 0; i < nslots; ++i) {
                     sv::mbar_wait(&b_empty[sb], pbp ^ 1);
-                    sv::mbar_arrive_expect_tx(&b_full[sb], (uint32_t)b_slot_bytes);
-                    sv::bulk_g2s(b_base + (size_t)sb * b_slot_bytes, wsrc + (size_t)i * b_slot_bytes, (uint32_t)b_slot_bytes,
-                                 &b_full[sb]);
+                    if ((p.dbg & 2) && (tile != (int)blockIdx.x || i >= p.n_b)) {
+                        sv::mbar_arrive(&b_full[sb]);
+                    } else {
+                        sv::mbar_arrive_expect_tx(&b_full[sb], (uint32_t)b_slot_bytes);
+                        sv::bulk_g2s(b_base + (size_t)sb * b_slot_bytes, wsrc + (size_t)i * b_slot_bytes, (uint32_t)b_slot_bytes,
+                                     &b_full[sb]);
+                    }
                     if (++sb == p.n_b) {
                         sb = 0;
                         pbp ^= 1;
@@ -634,7 +629,8 @@ int hl_plan(const int* g, HaloPlan* pl) {
     }
     pl->rows_alloc = (pl->rows + 31) & ~31;
     const int a_slot = 2 * pl->rows_alloc * 128;
-    const int fixed = (2 * HL_MAX_A + 2 * HL_MAX_B + 4) * 8 + 16 + HL_EPI_WARPS * 512 * 4 + 2 * pl->kchunks * 64 * 4 + 1024 + 64;
+    const int fixed = (2 * HL_MAX_A + 2 * HL_MAX_B + 4) * 8 + 16 + HL_EPI_WARPS * 512 * 4 + 2 * pl->kchunks * 64 * 4 +
+                      HL_EPI_WARPS * sv::EPI_STAGE_BYTES + 128 + 1024 + 64;
     const int budget = 227 * 1024 - fixed;
     for (int nt = (cd + 255) / 256; nt <= 16; ++nt) {
         int per = (cd + nt - 1) / nt;
@@ -643,11 +639,11 @@ int hl_plan(const int* g, HaloPlan* pl) {
         int n_a = 2;
         int n_b = (budget - n_a * a_slot) / b_slot;
         if (n_b < 2) continue;
-        if (n_b > HL_MAX_B) n_b = HL_MAX_B;
+        if (n_b > HL_MAX_B / 2) n_b = HL_MAX_B / 2;
         if (n_b >= 4 && budget - 3 * a_slot - 4 * b_slot >= 0) {   // room for a third A slot
             n_a = 3;
             n_b = (budget - n_a * a_slot) / b_slot;
-            if (n_b > HL_MAX_B) n_b = HL_MAX_B;
+            if (n_b > HL_MAX_B / 2) n_b = HL_MAX_B / 2;
         }
         pl->bnt = per;
         pl->ntiles = nt;
@@ -730,6 +726,12 @@ static int hl_launch(const HaloPlan& pl, HaloParams& p, int flags, void* stream)
     p.m_tiles = pl.m_tiles; p.bnt = pl.bnt; p.ntiles = pl.ntiles; p.kchunks = pl.kchunks; p.taps = pl.taps;
     p.n_a = pl.n_a; p.n_b = pl.n_b;
     p.use_base_off = (flags & 1) ? 1 : 0;
+    p.dbg = flags & (2 | 4 | 8);
+    p.b_split = (flags & 16) ? 1 : 0;   // measured: no gain (tools/halo_diag.py), kept as a switch
+    if (p.b_split) {
+        p.n_b = 2 * pl.n_b;
+        if (p.n_b > HL_MAX_B) p.n_b = HL_MAX_B;
+    }
     uint32_t cols = 32;
     while ((int)cols < 2 * p.bnt) cols <<= 1;
     p.tmem_cols = cols;

@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_bf16_kernel(const DgradPa
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     int* tap_dt = reinterpret_cast<int*>(tmem_slot + 2);
     int* tap_off = tap_dt + DG_MAX_TAPS;
+    unsigned char* s_stage = reinterpret_cast<unsigned char*>(   // [EPI_WARPS] x (32 rows x 128 B | 32 row indices)
+        (reinterpret_cast<uintptr_t>(tap_off + DG_MAX_TAPS) + 127) & ~(uintptr_t)127);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int taps = p.kt * p.kh * p.kw;
@@ -217,7 +219,9 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_bf16_kernel(const DgradPa
     } else if (warp < DG_EPI_WARPS) {
         // ------------------------------------------------------------------ epilogue
         const int quad = warp;
-        const int units = p.bnt >> 4;
+        unsigned char* my_stage = s_stage + (size_t)warp * sv::EPI_STAGE_BYTES;
+        const uint32_t stg = sv::smem_u32(my_stage);
+        int* row_pix = reinterpret_cast<int*>(my_stage + 32 * 128);
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_bf16_kernel(const DgradPa
             const DgClass& cl = p.cls[ci];
             const int mc = (m_tile - cl.tile_begin) * DG_BM + quad * 32 + lane;   // row inside the class
             const bool row_ok = mc < cl.pixels;
-            int m = 0;
+            int m = -1;
             if (row_ok) {
                 const int iw = mc % cl.n[2];
                 const int t1 = mc / cl.n[2];
@@ -237,42 +241,24 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_bf16_kernel(const DgradPa
                 const int n_ = t2 / cl.n[0];
                 m = ((n_ * p.td + cl.o[0] + it_ * p.st) * p.hd + cl.o[1] + ih * p.sh) * p.wd + cl.o[2] + iw * p.sw;
             }
+            row_pix[lane] = m;
+            __syncwarp();
             const int n_base = ntile * p.bnt;
-            float* out_row = p.dst + (size_t)m * p.cd;
             sv::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
             sv::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * (p.tmem_cols >> 1);
-            for (int u = 0; u < units; ++u) {
-                uint32_t av[16];
-                sv::tmem_ld16(taddr + (uint32_t)(u * 16), av);
-                sv::tmem_ld_wait();
-                const int ncol = n_base + u * 16;
-                if (row_ok) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        if (ncol + i < p.cd) {
-                            float4* dp = reinterpret_cast<float4*>(out_row + ncol + i);
-                            float4 o = make_float4(__uint_as_float(av[i]), __uint_as_float(av[i + 1]), __uint_as_float(av[i + 2]),
-                                                   __uint_as_float(av[i + 3]));
-                            if (p.accumulate) {
-                                const float4 old = *dp;
-                                o.x += old.x;
-                                o.y += old.y;
-                                o.z += old.z;
-                                o.w += old.w;
-                            }
-                            *dp = o;
-                        }
-                    }
-                }
-            }
+            // coalesced drain through the per-warp staging tile, see sv::epi_drain_group
+            sv::epi_drain_tile(taddr, p.bnt, 1.f, row_ok, stg, row_pix, p.dst, p.cd, n_base, p.accumulate, true, nullptr, lane);
             sv::tc_fence_before();
             __syncwarp();
             if (lane == 0) sv::mbar_arrive(&tempty_bar[acc]);
         }
     } else if (warp == DG_MMA_WARP) {
-        if (lane == 0) {
+        // MMA issuer: converged warp, warp-uniform schedule, one elected lane issues (see conv.cu)
+        {
             const uint32_t idesc = sv::make_idesc_f16(DG_BM, p.bnt, 1, 1, 0, 0);  // bf16 x bf16, K-major
+            const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint64_t desc_fixed = sv::make_smem_desc_sw128(0, 16, 1024);
             int stage = 0, it = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -283,35 +269,39 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dgrad_bf16_kernel(const DgradPa
                 const int kstages = p.cls[ci].kstages;
                 sv::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
                 sv::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * (p.tmem_cols >> 1);
+                const uint32_t d_tmem = tm0 + (uint32_t)acc * (p.tmem_cols >> 1);
                 for (int ks = 0; ks < kstages; ++ks) {
                     sv::mbar_wait(&full_bar[stage], phase);
                     sv::tc_fence_after();
                     const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t a_lo = a_hi + DG_A_BYTES;
-                    const uint32_t b_hi = a_lo + DG_A_BYTES;
-                    const uint32_t b_lo = b_hi + b_tile_bytes;
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {   // 4 x (K = 16 bf16 = 32 bytes)
-                        const uint64_t da_hi = sv::make_smem_desc_sw128(a_hi + k4 * 32, 16, 1024);
-                        const uint64_t db_hi = sv::make_smem_desc_sw128(b_hi + k4 * 32, 16, 1024);
+                    // k-step k4 (K = 16 bf16 = 32 bytes) adds 2 to the descriptor's 16-byte-unit address field
+                    const uint64_t da_hi = desc_fixed | (uint64_t)((a_hi & 0x3FFFFu) >> 4);
+                    const uint64_t da_lo = da_hi + (uint64_t)(DG_A_BYTES >> 4);
+                    const uint64_t db_hi = da_lo + (uint64_t)(DG_A_BYTES >> 4);
+                    const uint64_t db_lo = db_hi + (uint64_t)(b_tile_bytes >> 4);
+                    if (sv::elect_one()) {
                         if (p.passes == 3) {
-                            const uint64_t da_lo = sv::make_smem_desc_sw128(a_lo + k4 * 32, 16, 1024);
-                            const uint64_t db_lo = sv::make_smem_desc_sw128(b_lo + k4 * 32, 16, 1024);
-                            sv::umma_f16(d_tmem, da_lo, db_hi, idesc, (ks | k4) ? 1u : 0u);
-                            sv::umma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
-                            sv::umma_f16(d_tmem, da_hi, db_hi, idesc, 1u);
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                sv::umma_f16(d_tmem, da_lo + 2 * k4, db_hi + 2 * k4, idesc, (uint32_t)(ks | k4));
+                                sv::umma_f16(d_tmem, da_hi + 2 * k4, db_lo + 2 * k4, idesc, 1u);
+                                sv::umma_f16(d_tmem, da_hi + 2 * k4, db_hi + 2 * k4, idesc, 1u);
+                            }
                         } else {
-                            sv::umma_f16(d_tmem, da_hi, db_hi, idesc, (ks | k4) ? 1u : 0u);
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4)
+                                sv::umma_f16(d_tmem, da_hi + 2 * k4, db_hi + 2 * k4, idesc, (uint32_t)(ks | k4));
                         }
+                        sv::umma_commit(&empty_bar[stage]);
                     }
-                    sv::umma_commit(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                sv::umma_commit(&tfull_bar[acc]);
+                if (sv::elect_one()) sv::umma_commit(&tfull_bar[acc]);
+                __syncwarp();
             }
         }
     } else {
@@ -491,7 +481,7 @@ extern "C" int selavi_conv_dgrad_bf16(const void* z_hi, const void* z_lo, float*
     while ((int)cols < 2 * p.bnt) cols <<= 1;
     p.tmem_cols = cols;
     const int stage_bytes = 2 * DG_A_BYTES + 2 * p.bnt * 128;
-    const int tail_bytes = (2 * DG_MAX_STAGES + 4) * 8 + 8 + 2 * DG_MAX_TAPS * 4 + 64;
+    const int tail_bytes = (2 * DG_MAX_STAGES + 4) * 8 + 8 + 2 * DG_MAX_TAPS * 4 + DG_EPI_WARPS * sv::EPI_STAGE_BYTES + 128 + 64;
     int stages = (227 * 1024 - 1024 - tail_bytes) / stage_bytes;
     if (stages > DG_MAX_STAGES) stages = DG_MAX_STAGES;
     if (stages < 2) return selavi_fail(-1, "conv_dgrad_bf16: tile does not fit shared memory");

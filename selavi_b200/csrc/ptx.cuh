@@ -219,4 +219,107 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N, int af
     return d;
 }
 
+
+// ---------------------------------------------------------------- coalesced accumulator drain
+// Bytes of per-warp staging the epilogues below need: 32 rows x 128 B of fp32 columns + 32 row indices.
+constexpr int EPI_STAGE_BYTES = 32 * 128 + 32 * 4;
+
+__device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_shared_f1(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// One warp drains GW (32 or 16) fp32 accumulator columns of its 32-lane TMEM quadrant.  TMEM hands every lane ITS row;
+// storing that directly makes each st.global.v4 touch 32 different 128-byte lines (measured: the layer-1 kernels were
+// bound by exactly this, tools/halo_diag.py "no store").  Here the GW columns go through a 4 KB XOR-swizzled staging
+// tile in shared memory, and the global stores (and the accumulate-mode reads) are issued with 4 (GW=32) or 8 (GW=16)
+// complete row segments per instruction.  The per-column sums for the following BatchNorm (sum z, sum z^2 over the 32
+// rows, invalid rows contribute exact zeros) are read off the same staging tile: lane c owns column c.
+//   taddr   : TMEM address of the first column (lane field = quadrant base)
+//   stg     : shared-memory address of this warp's staging tile, 128-byte aligned; row_pix = the 32 ints behind it
+//             (global row index of each TMEM lane, -1 = no such row), written by the caller + __syncwarp()
+//   col0    : destination column of the first accumulator column; columns >= cd are not stored
+//   stat    : this warp's [2][256] sum scratch, already offset to the group's first column; nullptr = no statistics
+template <int GW>
+__device__ __forceinline__ void epi_drain_group(uint32_t taddr, float oscale, bool row_ok, uint32_t stg, const int* row_pix,
+                                                float* __restrict__ dst, int cd, int col0, int accumulate, bool do_store,
+                                                float* stat, int lane);
+
+template <int GW>
+__device__ __forceinline__ void epi_drain_group(uint32_t taddr, float oscale, bool row_ok, uint32_t stg, const int* row_pix,
+                                                float* __restrict__ dst, int cd, int col0, int accumulate, bool do_store,
+                                                float* stat, int lane) {
+    static_assert(GW == 32 || GW == 16, "group width");
+    uint32_t av[GW];
+    if constexpr (GW == 32) tmem_ld32(taddr, av);
+    else tmem_ld16(taddr, av);
+    tmem_ld_wait();
+    const uint32_t my_row = stg + (uint32_t)lane * 128u;
+#pragma unroll
+    for (int j = 0; j < GW / 4; ++j) {
+        float f[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) f[e] = row_ok ? __uint_as_float(av[4 * j + e]) * oscale : 0.f;   // invalid rows: exact zeros
+        st_shared_f4(my_row + (uint32_t)((j ^ (lane & 7)) << 4), f[0], f[1], f[2], f[3]);
+    }
+    __syncwarp();
+    if (stat != nullptr && lane < GW) {
+        float s1 = 0.f, s2 = 0.f;
+        const uint32_t word = (uint32_t)(lane & 3) * 4u;
+        const int ch = lane >> 2;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            const float v = ld_shared_f1(stg + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4) + word);
+            s1 += v;
+            s2 = fmaf(v, v, s2);
+        }
+        stat[lane] = s1;
+        stat[256 + lane] = s2;
+    }
+    constexpr int CPR = GW / 4;      // 16-byte chunks per row segment
+    constexpr int RPI = 32 / CPR;    // row segments per store instruction
+    const int j = lane % CPR, rsub = lane / CPR;
+    const int col = col0 + j * 4;
+#pragma unroll
+    for (int i = 0; i < CPR; ++i) {   // 32 / RPI == CPR iterations
+        const int rr = i * RPI + rsub;
+        const int pix = row_pix[rr];
+        float4 v = ld_shared_f4(stg + (uint32_t)rr * 128u + (uint32_t)((j ^ (rr & 7)) << 4));
+        if (do_store && pix >= 0 && col < cd) {
+            float4* dp = reinterpret_cast<float4*>(dst + (size_t)pix * cd + col);
+            if (accumulate) {
+                const float4 old = *dp;
+                v.x += old.x;
+                v.y += old.y;
+                v.z += old.z;
+                v.w += old.w;
+            }
+            *dp = v;
+        }
+    }
+    __syncwarp();
+}
+
+// all bnt (multiple of 16) columns of one accumulator; stat = this warp's [2][256] scratch or nullptr
+__device__ __forceinline__ void epi_drain_tile(uint32_t taddr, int bnt, float oscale, bool row_ok, uint32_t stg, const int* row_pix,
+                                               float* __restrict__ dst, int cd, int n_base, int accumulate, bool do_store,
+                                               float* stat, int lane) {
+    int c0 = 0;
+    for (; c0 + 32 <= bnt; c0 += 32)
+        epi_drain_group<32>(taddr + (uint32_t)c0, oscale, row_ok, stg, row_pix, dst, cd, n_base + c0, accumulate, do_store,
+                            stat ? stat + c0 : nullptr, lane);
+    if (c0 < bnt)
+        epi_drain_group<16>(taddr + (uint32_t)c0, oscale, row_ok, stg, row_pix, dst, cd, n_base + c0, accumulate, do_store,
+                            stat ? stat + c0 : nullptr, lane);
+}
+
 }  // namespace sv

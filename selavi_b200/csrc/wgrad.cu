@@ -534,39 +534,45 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf
         }
         sv::tc_fence_before();
     } else {
-        if (lane == 0) {
+        // MMA issuer: converged warp, warp-uniform schedule, one elected lane issues (see conv.cu)
+        {
             const uint32_t idesc = sv::make_idesc_f16(128, p.bnt, 1, 1, 1, 1);  // bf16 x bf16, both MN-major
+            const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t a_sbo = 2 * 1024, b_sbo = (uint32_t)(nchb * 1024);
+            const uint64_t a_fixed = sv::make_smem_desc(0, 1024, a_sbo, 2), b_fixed = sv::make_smem_desc(0, 1024, b_sbo, 2);
             for (int i = 0; i < nks; ++i) {
                 sv::mbar_wait(&full_bar[stage], phase);
                 sv::tc_fence_after();
                 const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint32_t a_lo = a_hi + WB_A_BYTES;
-                const uint32_t b_hi = a_lo + WB_A_BYTES;
-                const uint32_t b_lo = b_hi + b_bytes;
+                // UMMA_K = 16 pixels = 2 k-groups of 8: step k16 advances the address field by 2 * sbo bytes
+                const uint64_t da_hi = a_fixed | (uint64_t)((a_hi & 0x3FFFFu) >> 4);
+                const uint64_t da_lo = da_hi + (uint64_t)(WB_A_BYTES >> 4);
+                const uint64_t db_hi = (b_fixed | (uint64_t)((a_hi & 0x3FFFFu) >> 4)) + (uint64_t)((2 * WB_A_BYTES) >> 4);
+                const uint64_t db_lo = db_hi + (uint64_t)(b_bytes >> 4);
+                const uint64_t a_step = (uint64_t)((2 * a_sbo) >> 4), b_step = (uint64_t)((2 * b_sbo) >> 4);
+                if (sv::elect_one()) {
 #pragma unroll
-                for (int k16 = 0; k16 < 2; ++k16) {   // UMMA_K = 16 pixels = 2 k-groups of 8
-                    const uint64_t da_hi = sv::make_smem_desc(a_hi + k16 * 2 * a_sbo, 1024, a_sbo, 2);
-                    const uint64_t db_hi = sv::make_smem_desc(b_hi + k16 * 2 * b_sbo, 1024, b_sbo, 2);
-                    if (p.passes == 3) {
-                        const uint64_t da_lo = sv::make_smem_desc(a_lo + k16 * 2 * a_sbo, 1024, a_sbo, 2);
-                        const uint64_t db_lo = sv::make_smem_desc(b_lo + k16 * 2 * b_sbo, 1024, b_sbo, 2);
-                        sv::umma_f16(tmem_base, da_lo, db_hi, idesc, (i | k16) ? 1u : 0u);
-                        sv::umma_f16(tmem_base, da_hi, db_lo, idesc, 1u);
-                        sv::umma_f16(tmem_base, da_hi, db_hi, idesc, 1u);
-                    } else {
-                        sv::umma_f16(tmem_base, da_hi, db_hi, idesc, (i | k16) ? 1u : 0u);
+                    for (int k16 = 0; k16 < 2; ++k16) {
+                        if (p.passes == 3) {
+                            sv::umma_f16(tm0, da_lo + k16 * a_step, db_hi + k16 * b_step, idesc, (uint32_t)(i | k16));
+                            sv::umma_f16(tm0, da_hi + k16 * a_step, db_lo + k16 * b_step, idesc, 1u);
+                            sv::umma_f16(tm0, da_hi + k16 * a_step, db_hi + k16 * b_step, idesc, 1u);
+                        } else {
+                            sv::umma_f16(tm0, da_hi + k16 * a_step, db_hi + k16 * b_step, idesc, (uint32_t)(i | k16));
+                        }
                     }
+                    sv::umma_commit(&empty_bar[stage]);
                 }
-                sv::umma_commit(&empty_bar[stage]);
+                __syncwarp();
                 if (++stage == p.stages) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
-            sv::umma_commit(accum_bar);
+            if (sv::elect_one()) sv::umma_commit(accum_bar);
+            __syncwarp();
         }
     }
     __syncthreads();
