@@ -349,11 +349,13 @@ struct WgradBf16Params {
     int kt, kh, kw, st, sh, sw, pt, ph, pw;
     int M;
     int mtiles, bnt, ntiles;
+    int G, groups;   // G consecutive 128-row tiles per CTA share every dz stage (one accumulator each)
     int stages, total_kstages, kstages_per_slice;
     int passes;
     uint32_t tmem_cols;
 };
 
+constexpr int WB_MAX_G = 3;
 constexpr int WB_LOADER_WARPS = 8;
 constexpr int WB_MMA_WARP = WB_LOADER_WARPS;
 constexpr int WB_THREADS = (WB_LOADER_WARPS + 1) * 32;
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int nchb = (p.bnt + 63) >> 6;              // 64-channel chunks of the B tile
     const int b_bytes = 4 * nchb * 1024;
-    const int stage_bytes = 2 * WB_A_BYTES + 2 * b_bytes;   // A_hi | A_lo | B_hi | B_lo
+    const int stage_bytes = p.G * 2 * WB_A_BYTES + 2 * b_bytes;   // G x (A_hi | A_lo) | B_hi | B_lo
     unsigned char* tail = smem + (size_t)p.stages * stage_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
     uint64_t* empty_bar = full_bar + 8;
@@ -382,8 +384,9 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int mt = blockIdx.x % p.mtiles;
-    const int ntile = blockIdx.x / p.mtiles;
+    const int mt0 = (blockIdx.x % p.groups) * p.G;
+    const int nmt = p.mtiles - mt0 < p.G ? p.mtiles - mt0 : p.G;   // 128-row tiles of this CTA
+    const int ntile = blockIdx.x / p.groups;
     const int slice = blockIdx.y;
     const int ks_begin = slice * p.kstages_per_slice;
     int ks_end = ks_begin + p.kstages_per_slice;
@@ -414,11 +417,14 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf
         // ---- A units (pixel, 8 GEMM rows): u = tid + 256*j, px = (tid >> 4) + 16*j, g8 = tid & 15; the 8 rows are the
         //      flattened K chunk (tap, c8) — fixed per thread for the whole kernel (cs is a multiple of 8)
         const int g8a = tid & 15;
-        const int Q8 = mt * 16 + g8a;
-        const int tap = Q8 / C8;
-        const int a_coff = (Q8 % C8) * 8;
-        const bool a_valid = tap < taps;
-        const int a_kw = tap % p.kw, a_kh = (tap / p.kw) % p.kh, a_kt = tap / (p.kw * p.kh);
+        int a_coff[WB_MAX_G], a_k[WB_MAX_G];   // per tile of the group: channel offset, packed tap (kt | kh<<8 | kw<<16) or -1
+#pragma unroll
+        for (int g = 0; g < WB_MAX_G; ++g) {
+            const int Q8 = (mt0 + g) * 16 + g8a;
+            const int tap = Q8 / C8;
+            a_coff[g] = (Q8 % C8) * 8;
+            a_k[g] = (g < nmt && tap < taps) ? ((tap / (p.kw * p.kh)) | (((tap / p.kw) % p.kh) << 8) | ((tap % p.kw) << 16)) : -1;
+        }
         uint32_t a_soff[2];
         int cw[2], ch_[2], ct[2], cn[2];
 #pragma unroll
@@ -455,21 +461,25 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf
         for (int i = 0; i < nks; ++i) {
             const int ks = ks_begin + i;
             sv::mbar_wait(&empty_bar[stage], phase ^ 1);
-            const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint32_t a_lo = a_hi + WB_A_BYTES;
-            const uint32_t b_hi = a_lo + WB_A_BYTES;
+            const uint32_t a_base = sv::smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t b_hi = a_base + (uint32_t)(p.G * 2 * WB_A_BYTES);
             const uint32_t b_lo = b_hi + b_bytes;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int m = ks * WG_PIX + (tid >> 4) + 16 * j;
-                const int a = ct[j] * p.st - p.pt + a_kt;
-                const int b = ch_[j] * p.sh - p.ph + a_kh;
-                const int d = cw[j] * p.sw - p.pw + a_kw;
-                const bool ok = a_valid & (m < p.M) & (a >= 0) & (a < p.ts) & (b >= 0) & (b < p.hs) & (d >= 0) & (d < p.ws);
-                const size_t off = ok ? ((size_t)(((cn[j] * p.ts + a) * p.hs + b) * p.ws + d) * p.cs + a_coff) : 0;
-                const uint32_t nbytes = ok ? 16u : 0u;
-                cp_async16(a_hi + a_soff[j], p.a_hi + off, nbytes);
-                if (with_lo) cp_async16(a_lo + a_soff[j], p.a_lo + off, nbytes);
+                const int a0 = ct[j] * p.st - p.pt, b0 = ch_[j] * p.sh - p.ph, d0 = cw[j] * p.sw - p.pw;
+#pragma unroll
+                for (int g = 0; g < WB_MAX_G; ++g) {
+                    if (g < nmt) {
+                        const int a = a0 + (a_k[g] & 0xff), b = b0 + ((a_k[g] >> 8) & 0xff), d = d0 + ((a_k[g] >> 16) & 0xff);
+                        const bool ok = (a_k[g] >= 0) & (m < p.M) & (a >= 0) & (a < p.ts) & (b >= 0) & (b < p.hs) & (d >= 0) & (d < p.ws);
+                        const size_t off = ok ? ((size_t)(((cn[j] * p.ts + a) * p.hs + b) * p.ws + d) * p.cs + a_coff[g]) : 0;
+                        const uint32_t nbytes = ok ? 16u : 0u;
+                        const uint32_t a_hi = a_base + (uint32_t)(g * 2 * WB_A_BYTES);
+                        cp_async16(a_hi + a_soff[j], p.a_hi + off, nbytes);
+                        if (with_lo) cp_async16(a_hi + WB_A_BYTES + a_soff[j], p.a_lo + off, nbytes);
+                    }
+                }
                 cw[j] += WG_PIX;  // advance this pixel by one stage
                 while (cw[j] >= p.wd) {
                     cw[j] -= p.wd;
@@ -520,16 +530,18 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf
         const int u_end = half == 0 ? (units + 1) / 2 : units;
         const int row = quad * 32 + lane;
         const int ntot = p.ntiles * p.bnt;
-        float* out_row = p.partial + ((size_t)slice * (p.mtiles * 128) + mt * 128 + row) * ntot + n_off;
-        for (int u = u_begin; u < u_end; ++u) {
-            uint32_t acc[16];
-            sv::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(u * 16), acc);
-            sv::tmem_ld_wait();
+        for (int g = 0; g < nmt; ++g) {
+            float* out_row = p.partial + ((size_t)slice * (p.mtiles * 128) + (mt0 + g) * 128 + row) * ntot + n_off;
+            for (int u = u_begin; u < u_end; ++u) {
+                uint32_t acc[16];
+                sv::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * p.bnt + u * 16), acc);
+                sv::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-                *reinterpret_cast<float4*>(out_row + u * 16 + i) =
-                    make_float4(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]),
-                                __uint_as_float(acc[i + 3]));
+                for (int i = 0; i < 16; i += 4) {
+                    *reinterpret_cast<float4*>(out_row + u * 16 + i) =
+                        make_float4(__uint_as_float(acc[i]), __uint_as_float(acc[i + 1]), __uint_as_float(acc[i + 2]),
+                                    __uint_as_float(acc[i + 3]));
+                }
             }
         }
         sv::tc_fence_before();
@@ -545,22 +557,28 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf
             for (int i = 0; i < nks; ++i) {
                 sv::mbar_wait(&full_bar[stage], phase);
                 sv::tc_fence_after();
-                const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t a_base = sv::smem_u32(smem + (size_t)stage * stage_bytes);
                 // UMMA_K = 16 pixels = 2 k-groups of 8: step k16 advances the address field by 2 * sbo bytes
-                const uint64_t da_hi = a_fixed | (uint64_t)((a_hi & 0x3FFFFu) >> 4);
-                const uint64_t da_lo = da_hi + (uint64_t)(WB_A_BYTES >> 4);
-                const uint64_t db_hi = (b_fixed | (uint64_t)((a_hi & 0x3FFFFu) >> 4)) + (uint64_t)((2 * WB_A_BYTES) >> 4);
+                const uint64_t da0 = a_fixed | (uint64_t)((a_base & 0x3FFFFu) >> 4);
+                const uint64_t db_hi = (b_fixed | (uint64_t)((a_base & 0x3FFFFu) >> 4)) + (uint64_t)((p.G * 2 * WB_A_BYTES) >> 4);
                 const uint64_t db_lo = db_hi + (uint64_t)(b_bytes >> 4);
                 const uint64_t a_step = (uint64_t)((2 * a_sbo) >> 4), b_step = (uint64_t)((2 * b_sbo) >> 4);
                 if (sv::elect_one()) {
-#pragma unroll
-                    for (int k16 = 0; k16 < 2; ++k16) {
+                    for (int g = 0; g < nmt; ++g) {
+                        const uint64_t da_hi = da0 + (uint64_t)((g * 2 * WB_A_BYTES) >> 4);
+                        const uint64_t da_lo = da_hi + (uint64_t)(WB_A_BYTES >> 4);
+                        const uint32_t d_tmem = tm0 + (uint32_t)(g * p.bnt);
                         if (p.passes == 3) {
-                            sv::umma_f16(tm0, da_lo + k16 * a_step, db_hi + k16 * b_step, idesc, (uint32_t)(i | k16));
-                            sv::umma_f16(tm0, da_hi + k16 * a_step, db_lo + k16 * b_step, idesc, 1u);
-                            sv::umma_f16(tm0, da_hi + k16 * a_step, db_hi + k16 * b_step, idesc, 1u);
+#pragma unroll
+                            for (int k16 = 0; k16 < 2; ++k16) {
+                                sv::umma_f16(d_tmem, da_lo + k16 * a_step, db_hi + k16 * b_step, idesc, (uint32_t)(i | k16));
+                                sv::umma_f16(d_tmem, da_hi + k16 * a_step, db_lo + k16 * b_step, idesc, 1u);
+                                sv::umma_f16(d_tmem, da_hi + k16 * a_step, db_hi + k16 * b_step, idesc, 1u);
+                            }
                         } else {
-                            sv::umma_f16(tm0, da_hi + k16 * a_step, db_hi + k16 * b_step, idesc, (uint32_t)(i | k16));
+#pragma unroll
+                            for (int k16 = 0; k16 < 2; ++k16)
+                                sv::umma_f16(d_tmem, da_hi + k16 * a_step, db_hi + k16 * b_step, idesc, (uint32_t)(i | k16));
                         }
                     }
                     sv::umma_commit(&empty_bar[stage]);
@@ -610,15 +628,32 @@ void wg_tiles(int n_out, int* bnt, int* ntiles) {
 
 struct WgPlan {
     int mtiles, bnt, ntiles, natom, total_kstages, slices, kstages_per_slice;
+    int G, groups;   // bf16 kernel: G consecutive 128-row tiles per CTA (tf32 kernel: always 1 tile per CTA)
 };
 
-WgPlan wg_plan(int co, int taps, int cs, long long M) {
+WgPlan wg_plan(int co, int taps, int cs, long long M, bool bf16) {
     WgPlan pl;
     wg_tiles(co, &pl.bnt, &pl.ntiles);
     pl.natom = (pl.bnt + 31) / 32;
     pl.mtiles = (taps * cs + 127) / 128;
     pl.total_kstages = (int)((M + WG_PIX - 1) / WG_PIX);
-    const int tiles = pl.mtiles * pl.ntiles;
+    // bf16 kernel: the CTAs of a group of G row tiles share every dz stage (the 4-5 row tiles of the layer-1 convs each
+    // re-read the whole gradient tensor from L2 otherwise); G is bounded by TMEM (G * bnt <= 512 columns) and by keeping
+    // at least 3 pipeline stages of G * 16 KB + the dz tile in shared memory
+    int G = 1;
+    if (bf16) {
+        const int b_stage = 2 * 4 * ((pl.bnt + 63) / 64) * 1024;
+        int gmax = 512 / pl.bnt;
+        const int gsmem = ((226 * 1024 - 256) / 3 - b_stage) / (2 * WB_A_BYTES);
+        if (gmax > gsmem) gmax = gsmem;
+        if (gmax > WB_MAX_G) gmax = WB_MAX_G;
+        if (gmax < 1) gmax = 1;
+        const int groups = (pl.mtiles + gmax - 1) / gmax;
+        G = (pl.mtiles + groups - 1) / groups;   // balanced groups
+    }
+    pl.G = G;
+    pl.groups = (pl.mtiles + G - 1) / G;
+    const int tiles = pl.groups * pl.ntiles;
     int slices = (148 * 3) / tiles;  // at most 3 full waves of CTAs (no tail wave)
     if (slices < 1) slices = 1;
     if (slices > pl.total_kstages) slices = pl.total_kstages;
@@ -641,8 +676,9 @@ extern "C" size_t selavi_wgrad_workspace_bytes(const int* geom) {
     const long long M = (long long)geom[1] * geom[6] * geom[7] * geom[8];
     const long long Min = (long long)geom[1] * geom[2] * geom[3] * geom[4];
     const int taps = geom[10] * geom[11] * geom[12];
-    const WgPlan pl = wg_plan(geom[19], taps, geom[5], M);
-    const size_t partial = (size_t)pl.slices * pl.mtiles * 128 * pl.ntiles * pl.bnt * sizeof(float);
+    const WgPlan pl = wg_plan(geom[19], taps, geom[5], M, true), pl32 = wg_plan(geom[19], taps, geom[5], M, false);
+    const int slices = pl.slices > pl32.slices ? pl.slices : pl32.slices;
+    const size_t partial = (size_t)slices * pl.mtiles * 128 * pl.ntiles * pl.bnt * sizeof(float);
     return align256(partial) + 2 * align256((size_t)Min * geom[5] * 2) + 2 * align256((size_t)M * geom[9] * 2) + 256;
 }
 
@@ -678,24 +714,24 @@ int wgrad_run(const float* src, const float* dz, const void* z_hi_in, const void
     if (M <= 0 || M > 0x7fffffffLL || Min > 0x7fffffffLL) return selavi_fail(-1, "conv_wgrad: bad pixel count");
     p.M = (int)M;
     const int taps = p.kt * p.kh * p.kw;
-    const WgPlan pl = wg_plan(co, taps, p.cs, M);
+    const bool bf16 = passes < 10;
+    const WgPlan pl = wg_plan(co, taps, p.cs, M, bf16);
     p.mtiles = pl.mtiles; p.bnt = pl.bnt; p.ntiles = pl.ntiles; p.natom = pl.natom;
     p.total_kstages = pl.total_kstages; p.kstages_per_slice = pl.kstages_per_slice;
     p.pro_relu = pro_relu;
-    const bool bf16 = passes < 10;
     if (!bf16 && !dz) return selavi_fail(-1, "conv_wgrad: the tf32 path needs the fp32 gradient");
     p.passes = bf16 ? passes : passes - 10;
     uint32_t cols = 32;
-    while ((int)cols < p.bnt) cols <<= 1;
+    while ((int)cols < pl.G * p.bnt) cols <<= 1;
     p.tmem_cols = cols;
-    const int stage_bytes = bf16 ? 2 * WB_A_BYTES + 2 * 4 * ((p.bnt + 63) / 64) * 1024 : 2 * WG_A_BYTES + 2 * p.bnt * 128;
+    const int stage_bytes = bf16 ? pl.G * 2 * WB_A_BYTES + 2 * 4 * ((p.bnt + 63) / 64) * 1024 : 2 * WG_A_BYTES + 2 * p.bnt * 128;
     const int tail_bytes = 8 * 8 * 2 + 8 + 8 + 64;
     int stages = (227 * 1024 - 1024 - tail_bytes) / stage_bytes;
     if (stages > 6) stages = 6;
     if (stages < 2) return selavi_fail(-1, "conv_wgrad: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + tail_bytes + 1024;
-    dim3 grid(pl.mtiles * pl.ntiles, pl.slices);
+    dim3 grid(pl.groups * pl.ntiles, pl.slices);
     if (bf16) {
         // operand preparation: normalise + split the conv input (and dz unless it arrives pre-split): one HBM pass each
         const size_t partial_bytes = align256((size_t)pl.slices * pl.mtiles * 128 * pl.ntiles * pl.bnt * sizeof(float));
@@ -723,6 +759,7 @@ int wgrad_run(const float* src, const float* dz, const void* z_hi_in, const void
         q.td = p.td; q.hd = p.hd; q.wd = p.wd; q.cd = p.cd;
         q.kt = p.kt; q.kh = p.kh; q.kw = p.kw; q.st = p.st; q.sh = p.sh; q.sw = p.sw; q.pt = p.pt; q.ph = p.ph; q.pw = p.pw;
         q.M = p.M; q.mtiles = p.mtiles; q.bnt = p.bnt; q.ntiles = p.ntiles;
+        q.G = pl.G; q.groups = pl.groups;
         q.stages = p.stages; q.total_kstages = p.total_kstages; q.kstages_per_slice = p.kstages_per_slice;
         q.passes = p.passes; q.tmem_cols = p.tmem_cols;
         SV_CUDA_CHECK(cudaFuncSetAttribute(wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),

@@ -165,10 +165,9 @@ def halo_plan(geom, mode=0):
                     pays = geom.kt == 3 or geom.wi >= 12
                 else:
                     # data gradient (cp.async-fed in both kernels): the tap-reuse kernel wins on the temporal convs with
-                    # at least one full 8-frame block (1.3-2.1x) and on the small-frame spatial convs (1.1-1.7x); on the
-                    # 56x56 / 28x28 spatial convs both are bound by streaming the weight tiles from L2 and the implicit
-                    # GEMM's exact K packing is ~5 % ahead
-                    pays = geom.ti >= 8 if geom.kt == 3 else geom.wi <= 14
+                    # at least one full 8-frame block (1.3-2.1x) and, since the coalesced accumulator drain, on every
+                    # spatial conv (layer-1 64<-144: 1.06 ms vs 1.7 ms, gpurun r01k)
+                    pays = geom.ti >= 8 if geom.kt == 3 else True
             if pays:
                 plan = (mt.value, bnt.value, nt.value, wb.value)
     geom.__dict__[key] = plan
