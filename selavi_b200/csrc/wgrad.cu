@@ -13,6 +13,7 @@
 // order and scatters into the torch weight layout (deterministic, no atomics).
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/selavi_b200.h"
 #include "common.cuh"
@@ -601,18 +602,32 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf
 }
 
 // dW[co][ci][tap] (+)= sum_s partial[s][tap*cs + ci][co]
+// swapped (operands exchanged, see wgrad_run): partial[s][(taps-1-tap)*rs + co][ci], rs = channel stride of dz
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int slices, int mg_pad, int ntot, int co, int ci,
-                                    int taps, int cs, float* __restrict__ dW, int accumulate) {
+                                    int taps, int rs, int swapped, float* __restrict__ dW, int accumulate) {
     const size_t total = (size_t)co * ci * taps;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        // co fastest for coalesced reads of the partial tiles
-        const int o = (int)(idx % co);
-        const size_t r = idx / co;
-        const int c = (int)(r % ci);
-        const int tap = (int)(r / ci);
-        const size_t row = (size_t)tap * cs + c;
+        // the column index of the partial tiles runs fastest (coalesced reads)
+        int o, c, tap;
+        size_t row;
+        int col;
+        if (!swapped) {
+            o = (int)(idx % co);
+            const size_t r = idx / co;
+            c = (int)(r % ci);
+            tap = (int)(r / ci);
+            row = (size_t)tap * rs + c;
+            col = o;
+        } else {
+            c = (int)(idx % ci);
+            const size_t r = idx / ci;
+            o = (int)(r % co);
+            tap = (int)(r / co);
+            row = (size_t)(taps - 1 - tap) * rs + o;
+            col = c;
+        }
         float s = 0.f;
-        for (int k = 0; k < slices; ++k) s += partial[((size_t)k * mg_pad + row) * ntot + o];
+        for (int k = 0; k < slices; ++k) s += partial[((size_t)k * mg_pad + row) * ntot + col];
         float* dst = dW + ((size_t)o * ci + c) * taps + tap;
         *dst = accumulate ? (*dst + s) : s;
     }
@@ -678,7 +693,12 @@ extern "C" size_t selavi_wgrad_workspace_bytes(const int* geom) {
     const int taps = geom[10] * geom[11] * geom[12];
     const WgPlan pl = wg_plan(geom[19], taps, geom[5], M, true), pl32 = wg_plan(geom[19], taps, geom[5], M, false);
     const int slices = pl.slices > pl32.slices ? pl.slices : pl32.slices;
-    const size_t partial = (size_t)slices * pl.mtiles * 128 * pl.ntiles * pl.bnt * sizeof(float);
+    size_t partial = (size_t)slices * pl.mtiles * 128 * pl.ntiles * pl.bnt * sizeof(float);
+    {   // operands exchanged (wgrad_run picks it for some stride-1 convs): rows = taps * cd, columns = input channels
+        const WgPlan ps = wg_plan(geom[5], taps, geom[9], M, true);
+        const size_t alt = (size_t)ps.slices * ps.mtiles * 128 * ps.ntiles * ps.bnt * sizeof(float);
+        if (alt > partial) partial = alt;
+    }
     return align256(partial) + 2 * align256((size_t)Min * geom[5] * 2) + 2 * align256((size_t)M * geom[9] * 2) + 256;
 }
 
@@ -715,7 +735,25 @@ int wgrad_run(const float* src, const float* dz, const void* z_hi_in, const void
     p.M = (int)M;
     const int taps = p.kt * p.kh * p.kw;
     const bool bf16 = passes < 10;
-    const WgPlan pl = wg_plan(co, taps, p.cs, M, bf16);
+    WgPlan pl = wg_plan(co, taps, p.cs, M, bf16);
+    // Exchanged operands (bf16 kernel, stride-1 "same" convolutions): sum_px dz[px][co] x[px+tap][ci] = sum_q
+    // dz[q-tap][co] x[q][ci], i.e. the same kernel with dz as the tap-shifted row operand (rows = (flipped tap, co)) and
+    // x as the column operand (N = ci).  Pays when that gives fewer / better-shaped MMAs: one M=128 MMA costs about
+    // max(N/2 + 12, 59) clocks (tools/umma_rate.cu), so the 144->64 temporal convs of layer 1 run as 2 row tiles x N=144
+    // instead of 4 row tiles x N=64.
+    bool swapped = false;
+    if (bf16 && p.st == 1 && p.sh == 1 && p.sw == 1 && p.ts == p.td && p.hs == p.hd && p.ws == p.wd &&
+        2 * p.pt == p.kt - 1 && 2 * p.ph == p.kh - 1 && 2 * p.pw == p.kw - 1 && !getenv("SELAVI_WGRAD_NOSWAP")) {
+        const WgPlan ps = wg_plan(ci_real, taps, p.cd, M, true);
+        auto cost = [](const WgPlan& w) {
+            const double t = w.bnt / 2.0 + 12.0;
+            return (double)w.mtiles * w.ntiles * (t < 59.0 ? 59.0 : t);
+        };
+        if (cost(ps) < 0.9 * cost(pl)) {
+            swapped = true;
+            pl = ps;
+        }
+    }
     p.mtiles = pl.mtiles; p.bnt = pl.bnt; p.ntiles = pl.ntiles; p.natom = pl.natom;
     p.total_kstages = pl.total_kstages; p.kstages_per_slice = pl.kstages_per_slice;
     p.pro_relu = pro_relu;
@@ -757,6 +795,11 @@ int wgrad_run(const float* src, const float* dz, const void* z_hi_in, const void
         q.partial = p.partial;
         q.nb = p.nb; q.ts = p.ts; q.hs = p.hs; q.ws = p.ws; q.cs = p.cs;
         q.td = p.td; q.hd = p.hd; q.wd = p.wd; q.cd = p.cd;
+        if (swapped) {   // same geometry (stride 1, same padding), row operand = dz, column operand = x
+            const __nv_bfloat16 *xh = q.a_hi, *xl = q.a_lo;
+            q.a_hi = q.z_hi; q.a_lo = q.z_lo; q.z_hi = xh; q.z_lo = xl;
+            q.cs = p.cd; q.cd = p.cs;
+        }
         q.kt = p.kt; q.kh = p.kh; q.kw = p.kw; q.st = p.st; q.sh = p.sh; q.sw = p.sw; q.pt = p.pt; q.ph = p.ph; q.pw = p.pw;
         q.M = p.M; q.mtiles = p.mtiles; q.bnt = p.bnt; q.ntiles = p.ntiles;
         q.G = pl.G; q.groups = pl.groups;
@@ -775,7 +818,7 @@ int wgrad_run(const float* src, const float* dz, const void* z_hi_in, const void
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, pl.slices, pl.mtiles * 128, pl.ntiles * pl.bnt, co, ci_real, taps,
-                                                    p.cs, dW, accumulate);
+                                                    swapped ? p.cd : p.cs, swapped ? 1 : 0, dW, accumulate);
     SV_CUDA_CHECK(cudaGetLastError(), "conv_wgrad: reduce launch");
     return 0;
 }

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(160, 1) rate_kernel(Cfg c, long long* out_clk)
         sv::fence_barrier_init();
     }
     if (warp == 4) {
-        sv::tmem_alloc(&tmem_slot, 256);
+        sv::tmem_alloc(&tmem_slot, 512);
         sv::tmem_relinquish();
     }
     sv::fence_proxy_async();
@@ -52,13 +52,25 @@ __global__ void __launch_bounds__(160, 1) rate_kernel(Cfg c, long long* out_clk)
             if (sv::elect_one()) {
                 for (int i = 0; i < c.iters; ++i) {
                     uint64_t da = da0, db = db0;
-                    if (c.pattern >= 1) {
+                    if (c.pattern >= 1) {   // (pattern 4 alternates tm0/tm1/tm0 | tm0/tm1/tm0: two of three hand-offs switch accumulator)
                         const int k = i & 3;
                         da += 2 * k;
                         db += 2 * k;
                     }
                     if (c.pattern == 2) da += (uint64_t)(((i >> 2) % 9) * 8 * 58);   // row shift of 58 rows x 128 B per "tap"
-                    if (c.pattern == 3) {
+                    if (c.pattern == 4) {
+                        // x3 group, consecutive MMAs alternate between two accumulators (no back-to-back dependency)
+                        const uint32_t tm1 = tm0 + (uint32_t)c.N;
+                        if (c.kind == 0) {
+                            sv::umma_tf32(tm0, da + a_lo, db, idesc, 1u);
+                            sv::umma_tf32(tm1, da, db + b_lo, idesc, 1u);
+                            sv::umma_tf32(tm0, da, db, idesc, 1u);
+                        } else {
+                            sv::umma_f16(tm0, da + a_lo, db, idesc, 1u);
+                            sv::umma_f16(tm1, da, db + b_lo, idesc, 1u);
+                            sv::umma_f16(tm0, da, db, idesc, 1u);
+                        }
+                    } else if (c.pattern == 3) {
                         // the real x3 group: (a_lo,b_hi) (a_hi,b_lo) (a_hi,b_hi) on the same k
                         if (c.kind == 0) {
                             sv::umma_tf32(tm0, da + a_lo, db, idesc, 1u);
@@ -87,7 +99,7 @@ __global__ void __launch_bounds__(160, 1) rate_kernel(Cfg c, long long* out_clk)
     __syncthreads();
     if (warp == 4) {
         sv::tc_fence_after();
-        sv::tmem_dealloc(tmem_slot, 256);
+        sv::tmem_dealloc(tmem_slot, 512);
     }
 }
 
@@ -97,11 +109,11 @@ int main() {
     const size_t smem = 200 * 1024;
     cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int Ns[] = {32, 64, 128, 144, 192, 256};
-    const char* pat[] = {"same desc", "4 k-steps", "k-steps+tap shift", "x3 group (hi/lo planes)"};
-    for (int grid : {1, 148}) {
+    const char* pat[] = {"same desc", "4 k-steps", "k-steps+tap shift", "x3 group (hi/lo planes)", "x3 group, 2 accumulators"};
+    for (int grid : {148}) {
         for (int kind : {1, 0}) {
             for (int swz : {2, 0}) {
-                for (int pattern = 0; pattern < 4; ++pattern) {
+                for (int pattern = 0; pattern < 5; ++pattern) {
                     if (swz == 0 && pattern != 0) continue;
                     printf("grid %3d kind %s swizzle %d pattern '%s':", grid, kind ? "f16 " : "tf32", swz, pat[pattern]);
                     for (int N : Ns) {
@@ -115,7 +127,7 @@ int main() {
                         cudaMemcpy(h, d_clk, grid * sizeof(long long), cudaMemcpyDeviceToHost);
                         long long mx = 0;
                         for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
-                        const int n_mma = c.iters * (pattern == 3 ? 3 : 1);
+                        const int n_mma = c.iters * (pattern >= 3 ? 3 : 1);
                         const double per = (double)mx / n_mma;
                         const double floor_clk = kind ? N / 2.0 : N / 2.0;   // per K = 32 bytes in both kinds
                         printf("  N=%d %.1f clk (%.0f%%)", N, per, 100.0 * floor_clk / per);
