@@ -58,7 +58,6 @@ struct HaloParams {
     int n_a, n_b;
     int pro_relu, use_base_off;
     int src_kind, accumulate;
-    int b_split;                 // 1: hi and lo weight planes travel in separate pipeline slots (finer B pipeline)
     int dbg;                     // timing diagnostics only (results invalid): 2 no B reloads, 4 no A gathers, 8 no stores
     float oscale;
     uint32_t tmem_cols;
@@ -81,13 +80,18 @@ struct HlBatch {
     uint32_t ok;
 };
 
+// PAIR: the two CTAs of a cluster form a tcgen05 CTA pair (cta_group::2).  Each CTA still owns one 128-pixel tile (its own
+// input window, loaders, TMEM accumulators and epilogue) but the pair shares every weight tile: each CTA stages HALF of
+// its rows (N/2 output channels) and the leader CTA issues M=256 MMAs that read both halves and write both CTAs' TMEM.
+// That halves the weight bytes streamed into each SM and the shared-memory bytes the tensor core reads for B.
+template <bool PAIR>
 __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int a_plane = p.rows_alloc * 128;
     const int a_slot_bytes = 2 * a_plane;
-    const int b_plane = p.bnt * 128;
-    const int b_slot_bytes = p.b_split ? b_plane : 2 * b_plane;
+    const int b_plane = (PAIR ? p.bnt >> 1 : p.bnt) * 128;   // rows of the weight tile staged by this CTA
+    const int b_slot_bytes = 2 * b_plane;                     // hi | lo
     unsigned char* a_base = smem;
     unsigned char* b_base = a_base + (size_t)p.n_a * a_slot_bytes;
     unsigned char* tail = b_base + (size_t)p.n_b * b_slot_bytes;
@@ -95,7 +99,8 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
     uint64_t* a_empty = a_full + HL_MAX_A;
     uint64_t* b_full = a_empty + HL_MAX_A;
     uint64_t* b_empty = b_full + HL_MAX_B;
-    uint64_t* tfull_bar = b_empty + HL_MAX_B;
+    uint64_t* b_peer = b_empty + HL_MAX_B;    // PAIR, leader only: the peer CTA's half of slot s has landed
+    uint64_t* tfull_bar = b_peer + HL_MAX_B;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);   // [EPI_WARPS][2][256]
@@ -104,21 +109,38 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
         (reinterpret_cast<uintptr_t>(s_pro + 2 * p.kchunks * 64) + 127) & ~(uintptr_t)127);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int total_tiles = p.m_tiles * p.ntiles;
     const int ctab = p.kchunks * 64;
+    // work items: (m_tile, n_tile), or for a CTA pair (pair of consecutive m_tiles, n_tile); CTA `rank` of the pair takes
+    // m_tile 2*m_pair + rank (an odd tail recomputes the last tile and discards it: both CTAs run the same schedule)
+    const uint32_t rank = PAIR ? sv::cluster_ctarank() : 0u;
+    const int nwork = PAIR ? ((p.m_tiles + 1) >> 1) * p.ntiles : p.m_tiles * p.ntiles;
+    const int w_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int w_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto m_tile_of = [&](int w, bool& valid) {
+        int mt = w / p.ntiles;
+        valid = true;
+        if (PAIR) {
+            mt = 2 * mt + (int)rank;
+            valid = mt < p.m_tiles;
+            if (!valid) mt = p.m_tiles - 1;
+        }
+        return mt;
+    };
+    const int npair = PAIR ? 2 : 1;
 
     if (tid == 0) {
         for (int s = 0; s < p.n_a; ++s) {
-            sv::mbar_init(&a_full[s], HL_LOADER_WARPS);
+            sv::mbar_init(&a_full[s], HL_LOADER_WARPS * npair);   // PAIR: both CTAs' loaders arrive at the leader's
             sv::mbar_init(&a_empty[s], 1);
         }
         for (int s = 0; s < p.n_b; ++s) {
             sv::mbar_init(&b_full[s], 1);
             sv::mbar_init(&b_empty[s], 1);
+            sv::mbar_init(&b_peer[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             sv::mbar_init(&tfull_bar[a], 1);
-            sv::mbar_init(&tempty_bar[a], HL_EPI_WARPS);
+            sv::mbar_init(&tempty_bar[a], HL_EPI_WARPS * npair);
         }
         sv::fence_barrier_init();
     }
@@ -131,14 +153,28 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
         s_pro[i] = sc;
         s_pro[ctab + i] = sf;
     }
+    if (PAIR) {   // both CTAs' barriers are initialised (and both CTAs are running) before anything crosses the pair
+        __syncthreads();
+        sv::cluster_sync_all();
+    }
     if (warp == HL_MMA_WARP) {
-        sv::tmem_alloc(tmem_slot, p.tmem_cols);
-        sv::tmem_relinquish();
+        if (PAIR) {
+            sv::tmem_alloc_2cta(tmem_slot, p.tmem_cols);
+            sv::tmem_relinquish_2cta();
+        } else {
+            sv::tmem_alloc(tmem_slot, p.tmem_cols);
+            sv::tmem_relinquish();
+        }
     }
     sv::tc_fence_before();
     __syncthreads();
     sv::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // barrier arrivals that the pair's leader (rank 0) consumes
+    auto arrive_leader = [&](uint64_t* bar) {
+        if (PAIR) sv::mbar_arrive_cluster(sv::mapa_u32(sv::smem_u32(bar), 0u));
+        else sv::mbar_arrive(bar);
+    };
 
     if (warp >= HL_EPI_WARPS && warp < HL_MMA_WARP) {
         // ------------------------------------------------------------------ A loaders (256 threads)
@@ -149,8 +185,9 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
         const int nrow_thr = p.rows_alloc >> 5;
         const bool relu = p.pro_relu != 0;
         int pb[8];
-        auto setup = [&](int tile) {
-            const int m_tile = tile / p.ntiles;
+        auto setup = [&](int w) {
+            bool valid_;
+            const int m_tile = m_tile_of(w, valid_);
             if (p.mode == 0) {
                 const int sb = m_tile % p.SB;
                 const int t1 = m_tile / p.SB;
@@ -243,11 +280,11 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
         };
         int slot = 0;
         uint32_t phase = 0;
-        int tile = blockIdx.x, kc = 0;
+        int tile = w_first, kc = 0;   // tile = work item index
         if (p.src_kind == 1) {
             // pre-split bf16 planes: the slot is filled by zero-filling 16-byte cp.async copies, published one slot late
             int prev_slot = -1;
-            while (tile < total_tiles) {
+            while (tile < nwork) {
                 if (kc == 0) setup(tile);
                 sv::mbar_wait(&a_empty[slot], phase ^ 1);
                 const uint32_t a_hi = sv::smem_u32(a_base + (size_t)slot * a_slot_bytes);
@@ -271,7 +308,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
                     asm volatile("cp.async.wait_group 1;\n" ::: "memory");
                     sv::fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) sv::mbar_arrive(&a_full[prev_slot]);
+                    if (lane == 0) arrive_leader(&a_full[prev_slot]);
                 }
                 prev_slot = slot;
                 if (++slot == p.n_a) {
@@ -280,22 +317,22 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
                 }
                 if (++kc == p.kchunks) {
                     kc = 0;
-                    tile += gridDim.x;
+                    tile += w_step;
                 }
             }
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             sv::fence_proxy_async();
             __syncwarp();
-            if (lane == 0 && prev_slot >= 0) sv::mbar_arrive(&a_full[prev_slot]);
+            if (lane == 0 && prev_slot >= 0) arrive_leader(&a_full[prev_slot]);
         }
         HlBatch sa, sb;
         const bool no_a = (p.dbg & 4) != 0;
-        if (p.src_kind == 1) tile = total_tiles;
-        if (tile < total_tiles) {
+        if (p.src_kind == 1) tile = nwork;
+        if (tile < nwork) {
             setup(tile);
             if (!no_a) gather(sa, 0, 0);
         }
-        while (tile < total_tiles) {
+        while (tile < nwork) {
             if (!no_a) gather(sb, 4, kc);   // rows 4..7 of this slot in flight while rows 0..3 are converted
             sv::mbar_wait(&a_empty[slot], phase ^ 1);
             const uint32_t a_hi = sv::smem_u32(a_base + (size_t)slot * a_slot_bytes);
@@ -303,16 +340,16 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
             int ntile = tile, nkc = kc + 1;
             if (nkc == p.kchunks) {
                 nkc = 0;
-                ntile += gridDim.x;
+                ntile += w_step;
             }
-            if (ntile < total_tiles) {
+            if (ntile < nwork) {
                 if (ntile != tile) setup(ntile);
                 if (!no_a) gather(sa, 0, nkc);   // first rows of the NEXT slot in flight while rows 4..7 are converted
             }
             if (!no_a) commit(sb, 4, kc, a_hi);
             sv::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) sv::mbar_arrive(&a_full[slot]);
+            if (lane == 0) arrive_leader(&a_full[slot]);
             if (++slot == p.n_a) {
                 slot = 0;
                 phase ^= 1;
@@ -329,9 +366,10 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
         const uint32_t stg = sv::smem_u32(my_stage);
         int* row_pix = reinterpret_cast<int*>(my_stage + 32 * 128);
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int w = w_first; w < nwork; w += w_step, ++it) {
             const int acc = it & 1;
-            const int m_tile = tile / p.ntiles, ntile = tile % p.ntiles;
+            bool valid;
+            const int m_tile = m_tile_of(w, valid), ntile = w % p.ntiles;
             const int m = quad * 32 + lane;
             bool row_ok;
             int pix;
@@ -358,14 +396,14 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
             sv::mbar_wait(&tfull_bar[acc], (uint32_t)((it >> 1) & 1));
             sv::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * (p.tmem_cols >> 1);
-            sv::epi_drain_tile(taddr, p.bnt, p.oscale, row_ok, stg, row_pix, p.dst, p.cd, n_base, p.accumulate, !(p.dbg & 8),
-                               p.stats != nullptr ? my_stat : nullptr, lane);
+            sv::epi_drain_tile(taddr, p.bnt, p.oscale, row_ok, stg, row_pix, p.dst, p.cd, n_base, p.accumulate,
+                               valid && !(p.dbg & 8), p.stats != nullptr ? my_stat : nullptr, lane);
             sv::tc_fence_before();
             __syncwarp();
-            if (lane == 0) sv::mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) arrive_leader(&tempty_bar[acc]);
             if (p.stats != nullptr) {
                 hl_named_bar_sync(1, HL_EPI_WARPS * 32);
-                for (int i = tid; i < 2 * p.bnt; i += HL_EPI_WARPS * 32) {
+                for (int i = tid; i < 2 * p.bnt && valid; i += HL_EPI_WARPS * 32) {
                     const int which = i >= p.bnt, col = which ? i - p.bnt : i;
                     float tsum = 0.f;
 #pragma unroll
@@ -380,15 +418,40 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
         // The whole warp walks the schedule converged (all values warp-uniform, so descriptors live in uniform
         // registers) and one elected lane issues: under a divergent `if (lane == 0)` the compiler has to wrap every
         // tcgen05.mma in an elect / register-broadcast / branch loop, which made the ISSUE the bottleneck (~180 clk per
-        // MMA on every layer, profiles/r01i_halo_diag.txt).
-        {
+        // MMA on every layer); tools/umma_rate.cu: N/2 clk per MMA needs a tight unrolled issue sequence.
+        if (PAIR && rank != 0) {
+            // peer CTA of a pair: its MMAs are issued by the leader.  This warp only relays "my half of weight slot s has
+            // landed" (a local TMA completion) to the leader's b_peer[s].
+            int sb = 0;
+            uint32_t pbp = 0;
+            for (int w = w_first; w < nwork; w += w_step) {
+                const int nslots = p.kchunks * p.taps;
+                for (int i = 0; i < nslots; ++i) {
+                    sv::mbar_wait(&b_full[sb], pbp);
+                    if (lane == 0) sv::mbar_arrive_cluster(sv::mapa_u32(sv::smem_u32(&b_peer[sb]), 0u));
+                    __syncwarp();
+                    if (++sb == p.n_b) {
+                        sb = 0;
+                        pbp ^= 1;
+                    }
+                }
+            }
+        } else {
             const int fmt = p.src_kind == 1 ? 1 : 0;   // fp16 x fp16 (forward) or bf16 x bf16 (data gradient), K-major
-            const uint32_t idesc = sv::make_idesc_f16(128, p.bnt, fmt, fmt, 0, 0);
+            const uint32_t idesc = sv::make_idesc_f16(PAIR ? 256 : 128, p.bnt, fmt, fmt, 0, 0);
             const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint64_t desc_fixed = sv::make_smem_desc_sw128(0, 16, 1024);
+            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t accumulate) {
+                if (PAIR) sv::umma_f16_2cta(d, da, db, idesc, accumulate);
+                else sv::umma_f16(d, da, db, idesc, accumulate);
+            };
+            auto commit = [&](uint64_t* bar) {   // (PAIR: the barrier at this offset in both CTAs)
+                if (PAIR) sv::umma_commit_2cta(bar);
+                else sv::umma_commit(bar);
+            };
             int sa = 0, sb = 0, it = 0;
             uint32_t pa = 0, pbp = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int w = w_first; w < nwork; w += w_step, ++it) {
                 const int acc = it & 1;
                 sv::mbar_wait(&tempty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
                 sv::tc_fence_after();
@@ -408,66 +471,42 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
                         if (p.use_base_off) da_hi |= (uint64_t)((a_tap >> 7) & 7u) << 49;
                         const uint64_t da_lo = da_hi + (uint64_t)(a_plane >> 4);
                         sv::mbar_wait(&b_full[sb], pbp);
+                        if (PAIR) sv::mbar_wait(&b_peer[sb], pbp);
                         sv::tc_fence_after();
                         const uint32_t b_hi = sv::smem_u32(b_base + (size_t)sb * b_slot_bytes);
                         const uint64_t db_hi = desc_fixed | (uint64_t)((b_hi & 0x3FFFFu) >> 4);
-                        if (p.b_split) {
-                            // hi plane: the two products that read it; then the lo plane from the next slot
-                            if (sv::elect_one()) {
-                                for (int k = 0; k < nk16; ++k) {
-                                    sv::umma_f16(d_tmem, da_lo + 2 * k, db_hi + 2 * k, idesc, started | (uint32_t)k);
-                                    sv::umma_f16(d_tmem, da_hi + 2 * k, db_hi + 2 * k, idesc, 1u);
-                                }
-                                sv::umma_commit(&b_empty[sb]);
-                            }
-                            __syncwarp();
-                            if (++sb == p.n_b) {
-                                sb = 0;
-                                pbp ^= 1;
-                            }
-                            sv::mbar_wait(&b_full[sb], pbp);
-                            sv::tc_fence_after();
-                            const uint32_t b_lo = sv::smem_u32(b_base + (size_t)sb * b_slot_bytes);
-                            const uint64_t db_lo = desc_fixed | (uint64_t)((b_lo & 0x3FFFFu) >> 4);
-                            if (sv::elect_one()) {
-                                for (int k = 0; k < nk16; ++k) sv::umma_f16(d_tmem, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
-                                sv::umma_commit(&b_empty[sb]);
-                            }
-                            __syncwarp();
-                        } else {
-                            const uint64_t db_lo = db_hi + (uint64_t)(b_plane >> 4);
-                            if (sv::elect_one()) {
-                                if (nk16 == 4) {   // full 64-channel chunk: 12 MMAs back to back, descriptor offsets folded
+                        const uint64_t db_lo = db_hi + (uint64_t)(b_plane >> 4);
+                        if (sv::elect_one()) {
+                            if (nk16 == 4) {   // full 64-channel chunk: 12 MMAs back to back, descriptor offsets folded
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        sv::umma_f16(d_tmem, da_lo + 2 * k, db_hi + 2 * k, idesc, started | (uint32_t)k);
-                                        sv::umma_f16(d_tmem, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
-                                        sv::umma_f16(d_tmem, da_hi + 2 * k, db_hi + 2 * k, idesc, 1u);
-                                    }
-                                } else {
-                                    for (int k = 0; k < nk16; ++k) {
-                                        sv::umma_f16(d_tmem, da_lo + 2 * k, db_hi + 2 * k, idesc, started | (uint32_t)k);
-                                        sv::umma_f16(d_tmem, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
-                                        sv::umma_f16(d_tmem, da_hi + 2 * k, db_hi + 2 * k, idesc, 1u);
-                                    }
+                                for (int k = 0; k < 4; ++k) {
+                                    mma(d_tmem, da_lo + 2 * k, db_hi + 2 * k, started | (uint32_t)k);
+                                    mma(d_tmem, da_hi + 2 * k, db_lo + 2 * k, 1u);
+                                    mma(d_tmem, da_hi + 2 * k, db_hi + 2 * k, 1u);
                                 }
-                                sv::umma_commit(&b_empty[sb]);
+                            } else {
+                                for (int k = 0; k < nk16; ++k) {
+                                    mma(d_tmem, da_lo + 2 * k, db_hi + 2 * k, started | (uint32_t)k);
+                                    mma(d_tmem, da_hi + 2 * k, db_lo + 2 * k, 1u);
+                                    mma(d_tmem, da_hi + 2 * k, db_hi + 2 * k, 1u);
+                                }
                             }
-                            __syncwarp();
+                            commit(&b_empty[sb]);
                         }
+                        __syncwarp();
                         if (++sb == p.n_b) {
                             sb = 0;
                             pbp ^= 1;
                         }
                     }
-                    if (sv::elect_one()) sv::umma_commit(&a_empty[sa]);
+                    if (sv::elect_one()) commit(&a_empty[sa]);
                     __syncwarp();
                     if (++sa == p.n_a) {
                         sa = 0;
                         pa ^= 1;
                     }
                 }
-                if (sv::elect_one()) sv::umma_commit(&tfull_bar[acc]);
+                if (sv::elect_one()) commit(&tfull_bar[acc]);
                 __syncwarp();
             }
         }
@@ -493,8 +532,9 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
             };
             // the input window of a tile is a few contiguous pixel ranges: pull the NEXT tile's window into L2 while
             // this one is processed, so that the loaders' gathers see L2 rather than DRAM latency
-            auto prefetch_tile = [&](int tile) {
-                const int m_tile = tile / p.ntiles;
+            auto prefetch_tile = [&](int w) {
+                bool valid_;
+                const int m_tile = m_tile_of(w, valid_);
                 if (p.mode == 0) {
                     const int sb = m_tile % p.SB;
                     const int t1 = m_tile / p.SB;
@@ -513,21 +553,28 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
                     if (h1 >= h0) prefetch_range((size_t)(f * p.H + h0) * p.W, (h1 - h0 + 1) * p.W);
                 }
             };
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const size_t full_plane = (size_t)p.bnt * 128;          // one hi (or lo) plane of a weight tile in HBM
+            const size_t half_off = PAIR ? (size_t)rank * b_plane : 0;   // this CTA's rows inside the plane
+            for (int w = w_first; w < nwork; w += w_step) {
                 // (measured: +7 % on the register-staged fp32 loaders, slightly negative on the cp.async-fed bf16 planes)
-                if (p.src_kind == 0 && tile + (int)gridDim.x < total_tiles && (p.ntiles == 1 || tile % p.ntiles == 0))
-                    prefetch_tile(tile + gridDim.x);
-                const int ntile = tile % p.ntiles;
-                const int nslots = p.kchunks * p.taps * (p.b_split ? 2 : 1);
-                const unsigned char* wsrc = p.wpack + (size_t)ntile * nslots * b_slot_bytes;
+                if (p.src_kind == 0 && w + w_step < nwork && (p.ntiles == 1 || w % p.ntiles == 0)) prefetch_tile(w + w_step);
+                const int ntile = w % p.ntiles;
+                const int nslots = p.kchunks * p.taps;
+                const unsigned char* wsrc = p.wpack + (size_t)ntile * nslots * 2 * full_plane;
                 for (int i = 0; i < nslots; ++i) {
                     sv::mbar_wait(&b_empty[sb], pbp ^ 1);
-                    if ((p.dbg & 2) && (tile != (int)blockIdx.x || i >= p.n_b)) {
+                    if ((p.dbg & 2) && (w != w_first || i >= p.n_b)) {
                         sv::mbar_arrive(&b_full[sb]);
                     } else {
+                        unsigned char* dst = b_base + (size_t)sb * b_slot_bytes;
+                        const unsigned char* src = wsrc + (size_t)i * 2 * full_plane + half_off;
                         sv::mbar_arrive_expect_tx(&b_full[sb], (uint32_t)b_slot_bytes);
-                        sv::bulk_g2s(b_base + (size_t)sb * b_slot_bytes, wsrc + (size_t)i * b_slot_bytes, (uint32_t)b_slot_bytes,
-                                     &b_full[sb]);
+                        if (PAIR) {   // rows [rank*N/2, (rank+1)*N/2) of the hi plane, then of the lo plane
+                            sv::bulk_g2s(dst, src, (uint32_t)b_plane, &b_full[sb]);
+                            sv::bulk_g2s(dst + b_plane, src + full_plane, (uint32_t)b_plane, &b_full[sb]);
+                        } else {
+                            sv::bulk_g2s(dst, src, (uint32_t)b_slot_bytes, &b_full[sb]);
+                        }
                     }
                     if (++sb == p.n_b) {
                         sb = 0;
@@ -538,9 +585,11 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
         }
     }
     __syncthreads();
+    if (PAIR) sv::cluster_sync_all();   // the peer may still be signalling this CTA's barriers / reading its shared memory
     if (warp == HL_MMA_WARP) {
         sv::tc_fence_after();
-        sv::tmem_dealloc(tmem_base, p.tmem_cols);
+        if (PAIR) sv::tmem_dealloc_2cta(tmem_base, p.tmem_cols);
+        else sv::tmem_dealloc(tmem_base, p.tmem_cols);
     }
 }
 
@@ -586,6 +635,8 @@ struct HaloPlan {
     int mode, nb, T, H, W, cs, cd, co, ci;
     int S, WP, TB, SB, OB, rows, rows_alloc, m_tiles, bnt, ntiles, kchunks, taps, n_a, n_b;
     size_t smem, wbytes;
+    int pair_ok, n_a2, n_b2;     // CTA-pair variant (cta_group::2): each CTA stages half of every weight tile
+    size_t smem2;
 };
 
 // geom: the 20-int geometry of selavi_conv_gemm (mode 0 forward, mode 1 data gradient: for these stride-1 "same"
@@ -629,7 +680,7 @@ int hl_plan(const int* g, HaloPlan* pl) {
     }
     pl->rows_alloc = (pl->rows + 31) & ~31;
     const int a_slot = 2 * pl->rows_alloc * 128;
-    const int fixed = (2 * HL_MAX_A + 2 * HL_MAX_B + 4) * 8 + 16 + HL_EPI_WARPS * 512 * 4 + 2 * pl->kchunks * 64 * 4 +
+    const int fixed = (2 * HL_MAX_A + 3 * HL_MAX_B + 4) * 8 + 16 + HL_EPI_WARPS * 512 * 4 + 2 * pl->kchunks * 64 * 4 +
                       HL_EPI_WARPS * sv::EPI_STAGE_BYTES + 128 + 1024 + 64;
     const int budget = 227 * 1024 - fixed;
     for (int nt = (cd + 255) / 256; nt <= 16; ++nt) {
@@ -651,6 +702,22 @@ int hl_plan(const int* g, HaloPlan* pl) {
         pl->n_b = n_b;
         pl->smem = (size_t)n_a * a_slot + (size_t)n_b * b_slot + fixed;
         pl->wbytes = (size_t)nt * pl->kchunks * pl->taps * b_slot;
+        // CTA pair: same tiling, half-size weight slots (N = per must be a multiple of 16 for M = 256: it is)
+        pl->pair_ok = pl->m_tiles >= 2 ? 1 : 0;
+        {
+            const int b_half = b_slot / 2;
+            int na2 = 2, nb2 = (budget - na2 * a_slot) / b_half;
+            if (nb2 > HL_MAX_B) nb2 = HL_MAX_B;
+            if (nb2 >= 6 && budget - 3 * a_slot - 6 * b_half >= 0) {
+                na2 = 3;
+                nb2 = (budget - na2 * a_slot) / b_half;
+                if (nb2 > HL_MAX_B) nb2 = HL_MAX_B;
+            }
+            if (nb2 < 2) pl->pair_ok = 0;
+            pl->n_a2 = na2;
+            pl->n_b2 = nb2;
+            pl->smem2 = (size_t)na2 * a_slot + (size_t)nb2 * b_half + fixed;
+        }
         return 0;
     }
     return 1;
@@ -727,22 +794,44 @@ static int hl_launch(const HaloPlan& pl, HaloParams& p, int flags, void* stream)
     p.n_a = pl.n_a; p.n_b = pl.n_b;
     p.use_base_off = (flags & 1) ? 1 : 0;
     p.dbg = flags & (2 | 4 | 8);
-    p.b_split = (flags & 16) ? 1 : 0;   // measured: no gain (tools/halo_diag.py), kept as a switch
-    if (p.b_split) {
-        p.n_b = 2 * pl.n_b;
-        if (p.n_b > HL_MAX_B) p.n_b = HL_MAX_B;
+    // flag 32: CTA pairs (cluster of 2, tcgen05 cta_group::2)
+    const bool pair = (flags & 32) && pl.pair_ok;
+    if (pair) {
+        p.n_a = pl.n_a2;
+        p.n_b = pl.n_b2;
     }
     uint32_t cols = 32;
     while ((int)cols < 2 * p.bnt) cols <<= 1;
     p.tmem_cols = cols;
-    SV_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem),
-                  "conv_halo: cudaFuncSetAttribute");
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (pair) {
+        SV_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem2),
+                      "conv_halo: cudaFuncSetAttribute");
+        const int nwork = ((p.m_tiles + 1) / 2) * p.ntiles;
+        int npairs = sms / 2;
+        if (npairs > nwork) npairs = nwork;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * npairs);
+        cfg.blockDim = dim3(HL_THREADS);
+        cfg.dynamicSmemBytes = pl.smem2;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<true>, p), "conv_halo: pair launch");
+        return 0;
+    }
+    SV_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem),
+                  "conv_halo: cudaFuncSetAttribute");
     const int total_tiles = p.m_tiles * p.ntiles;
     const int grid = total_tiles < sms ? total_tiles : sms;
-    conv_halo_kernel<<<grid, HL_THREADS, pl.smem, (cudaStream_t)stream>>>(p);
+    conv_halo_kernel<false><<<grid, HL_THREADS, pl.smem, (cudaStream_t)stream>>>(p);
     SV_CUDA_CHECK(cudaGetLastError(), "conv_halo: launch");
     return 0;
 }

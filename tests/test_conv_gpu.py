@@ -225,3 +225,54 @@ def test_conv_dgrad_halo(cuda_device, name, monkeypatch):
     assert err < 5e-5
     dx2 = ops.conv_dgrad_halo(z_hi, z_lo, wp, geom, out=dx.clone(), accumulate=True)
     assert _rel(dx2, 2 * dx) < 1e-6
+
+
+@pytest.mark.parametrize("name", sorted(HALO_LAYERS))
+def test_conv_halo_cta_pair_matches_single_cta(cuda_device, name, monkeypatch):
+    """CTA-pair variant (cluster of 2, tcgen05 cta_group::2, each CTA stages half of every weight tile): the MMAs see
+    the same operands in the same order, so forward (with prologue + stats) and data gradient are bit-identical to the
+    single-CTA kernel, including an odd number of pixel tiles (the pair's second CTA recomputes and discards)."""
+    from selavi_b200 import ops
+    monkeypatch.setattr(ops, "FWD_KERNEL", "halo")
+    x, w, geom, p = _mk_halo(name, cuda_device)
+    g = torch.Generator(device=cuda_device).manual_seed(5)
+    scale = torch.rand(geom.cis, device=cuda_device, generator=g) + 0.5
+    shift = torch.randn(geom.cis, device=cuda_device, generator=g) * 0.3
+    x_cl, wp = ops.to_channels_last(x), ops.pack_weights_halo(w, geom)
+    z_hi, z_lo = ops.split_bf16(torch.randn(geom.out_shape(), device=cuda_device, generator=g))
+    wpd = ops.pack_weights_halo(w, geom, mode=1)
+    out = {}
+    for flags in (0, 32):
+        monkeypatch.setattr(ops, "HALO_FLAGS", flags)
+        stats = ops.stats_buffer(geom, cuda_device, halo=True).zero_()
+        y = ops.conv_forward_halo(x_cl, wp, geom, scale=scale, shift=shift, relu=True, stats=stats)
+        dx = ops.conv_dgrad_halo(z_hi, z_lo, wpd, geom)
+        torch.cuda.synchronize()
+        out[flags] = (y, stats, dx)
+    for a, b in zip(out[0], out[32]):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["v_l1_temporal", "v_stem3_t", "v_l4_temporal_1152", "v_l3_spatial_288", "ragged_m"])
+def test_conv_wgrad_exchanged_operands(cuda_device, name, monkeypatch):
+    """bf16x3 weight gradient with the operands exchanged (dz as the tap-shifted row operand, picked by the cost model
+    for some stride-1 convs) against the plain orientation and the float64 reference."""
+    from selavi_b200 import ops
+    x, w, geom, (s, p) = _mk(name, cuda_device)
+    wd = w.double().requires_grad_(True)
+    ref_y = F.conv3d(x.double(), wd, None, s, p)
+    dz = torch.randn(ref_y.shape, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(11))
+    ref_dw, = torch.autograd.grad(ref_y, wd, dz.double())
+    z_hi, z_lo = ops.split_bf16(ops.to_channels_last(dz))
+    x_cl = ops.to_channels_last(x)
+    dws = []
+    for noswap in ("", "1"):
+        if noswap:
+            monkeypatch.setenv("SELAVI_WGRAD_NOSWAP", "1")
+        else:
+            monkeypatch.delenv("SELAVI_WGRAD_NOSWAP", raising=False)
+        dw = torch.full_like(w, float("nan"))
+        ops.conv_wgrad_bf16(x_cl, z_hi, z_lo, geom, dw)
+        assert _rel(dw, ref_dw) < 5e-5
+        dws.append(dw)
+    assert _rel(dws[0], dws[1]) < 2e-5

@@ -1,6 +1,6 @@
 """Where does the tap-reuse kernel's time go?  Times the layer-1 forward / data-gradient launches with parts of the
 kernel switched off (SELAVI_HALO_FLAGS debug bits: 2 = weights loaded once, 4 = no activation gathers, 8 = no output
-stores; 16 = hi and lo weight planes in separate pipeline slots).  Results of the debug variants are invalid by construction;
+stores; 32 = CTA pairs (cta_group::2)).  Results of the debug variants are invalid by construction;
 only their durations are read.  Not the bench contract."""
 import os
 import sys
@@ -26,7 +26,7 @@ def timeit(fn, warm=2, rep=5):
     return ts[len(ts) // 2]
 
 
-VARIANTS = [(0, "joint slots"), (16, "split slots"), (2, "no B"), (4, "no A"), (8, "no store"), (6, "no A,B"), (14, "MMA only")]
+VARIANTS = [(0, "single CTA"), (32, "CTA pair"), (2, "no B"), (4, "no A"), (8, "no store"), (14, "MMA only"), (32 | 14, "pair MMA only")]
 
 
 def run(name, ci, co, thw, k, nb=16):
@@ -54,8 +54,8 @@ def run(name, ci, co, thw, k, nb=16):
                 out = dx
             if flags == 0:
                 ref[kind] = out.clone()
-            if flags == 16:
-                row.append(f"[diff vs joint {float((out - ref[kind]).norm() / ref[kind].norm()):.1e}]")
+            if flags == 32:
+                row.append(f"[pair vs single {float((out - ref[kind]).norm() / ref[kind].norm()):.1e}]")
             row.append(f"{label} {ms:.3f} ms ({flop / ms / 1e9:.0f} TF/s)")
         ops.HALO_FLAGS = 0
         print(f"{name} {kind}: " + " | ".join(row), flush=True)
