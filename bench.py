@@ -152,7 +152,10 @@ def run_ours(args):
     opt = SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-5)    # main.py:132-137
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)  # main.py:156
+        ddp_kw = {}
+        if os.environ.get("SELAVI_DDP_BUCKET_MB"):   # (experiment knob; default = the reference's call, main.py:156-160)
+            ddp_kw["bucket_cap_mb"] = int(os.environ["SELAVI_DDP_BUCKET_MB"])
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True, **ddp_kw)
     video_h, spec_h, labels_h = synthetic_batch(torch, rank, B)
     video_h, spec_h, labels_h = video_h.pin_memory(), spec_h.pin_memory(), labels_h.pin_memory()
     video_d, spec_d, labels_d = video_h.to(dev), spec_h.to(dev), labels_h.to(dev)
