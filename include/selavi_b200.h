@@ -209,6 +209,16 @@ int selavi_mel_logfbank(const double* signal, int batch, long long samples, int 
                         const double* bins, int nfilt, int nfft, double preemph, int z_normalize, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Clip augmentation of the input pipeline (datasets/video_transforms.py:462-504 clip_augmentation with the default flags:
+ * x/255, -MEAN, /STD :474-477; bilinear short-side scale jitter :35-79; random / uniform crop :101-134,167-210; horizontal
+ * flip :137-164; THWC -> CTHW :480,503) in one pass.  frames uint8 [n][T][H][W][3] (device), out float32
+ * [n][3][T][crop][crop] (device); params is a HOST array [n][5] = (new_h, new_w, y_off, x_off, flip) per clip, drawn by
+ * the caller with the reference's np.random call order (selavi_b200/video_transforms.py).
+ */
+int selavi_clip_augment(const unsigned char* frames, float* out, int n, int T, int H, int W, int crop, const int* params,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Symmetric peer-mapped buffers (CUDA IPC), the transport of the in-kernel NVSwitch exchange.
  * alloc: cudaMalloc + zero + export a 64-byte handle; open/close: map / unmap a peer's handle.
  */

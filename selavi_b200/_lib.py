@@ -87,6 +87,7 @@ SIGNATURES = {
     "selavi_sgd_step_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_int, c_void_p]),
     "selavi_mel_logfbank": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p, c_int, c_int, c_double, c_int,
                                     c_void_p, c_void_p]),
+    "selavi_clip_augment": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "selavi_debug_umma_probe": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.c_ulonglong, ctypes.c_ulonglong,
                                         ctypes.c_uint, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "selavi_symm_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
@@ -113,7 +114,7 @@ KERNELS_PER_CALL = {
     "selavi_heads_bn_bwd_apply": 1, "selavi_heads_sum_masked": 1, "selavi_heads_colsum": 1, "selavi_ce_loss": 2,
     "selavi_debug_umma_probe": 1, "selavi_mel_logfbank": 1, "selavi_split_bf16": 1, "selavi_p2p_allreduce_f64": 1, "selavi_conv_wgrad_bf16": 3,
     "selavi_dgrad_pack_weights": 1, "selavi_conv_dgrad_bf16": 1,
-    "selavi_conv_halo_pack_weights": 1, "selavi_conv_halo_fwd": 1, "selavi_conv_halo_dgrad": 1,
+    "selavi_conv_halo_pack_weights": 1, "selavi_conv_halo_fwd": 1, "selavi_conv_halo_dgrad": 1, "selavi_clip_augment": 1,
 }
 COUNT_CALLS = False
 CALLS = {}
