@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
     uint64_t* tfull_bar = b_peer + HL_MAX_B;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    float* s_stat = reinterpret_cast<float*>(tmem_slot + 4);   // [EPI_WARPS][2][256]
+    float* s_stat = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [EPI_WARPS][2][256]
     float* s_pro = s_stat + HL_EPI_WARPS * 512;                 // [2][kchunks*64]: scale*16 | shift*16
     unsigned char* s_stage = reinterpret_cast<unsigned char*>(     // [EPI_WARPS] x (32 rows x 128 B | 32 row indices)
         (reinterpret_cast<uintptr_t>(s_pro + 2 * p.kchunks * 64) + 127) & ~(uintptr_t)127);
@@ -681,7 +681,7 @@ int hl_plan(const int* g, HaloPlan* pl) {
     pl->rows_alloc = (pl->rows + 31) & ~31;
     const int a_slot = 2 * pl->rows_alloc * 128;
     const int fixed = (2 * HL_MAX_A + 3 * HL_MAX_B + 4) * 8 + 16 + HL_EPI_WARPS * 512 * 4 + 2 * pl->kchunks * 64 * 4 +
-                      HL_EPI_WARPS * sv::EPI_STAGE_BYTES + 128 + 1024 + 64;
+                      HL_EPI_WARPS * sv::EPI_STAGE_BYTES + 128 + 16 + 1024 + 64;
     const int budget = 227 * 1024 - fixed;
     for (int nt = (cd + 255) / 256; nt <= 16; ++nt) {
         int per = (cd + nt - 1) / nt;

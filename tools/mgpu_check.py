@@ -49,6 +49,15 @@ def main():
     # ---- 2. DDP + SyncBN == single GPU on the full batch
     name = "mini_cfg2"
     video, spec, labels = make_inputs(name)
+    if video.shape[0] % world or video.shape[0] < world:
+        # more ranks than golden clips: tile the golden batch with per-copy gains (keeps BatchNorm well conditioned)
+        reps = -(-world // video.shape[0])
+        gains = np.linspace(0.6, 1.7, reps, dtype=np.float32)
+        video = np.concatenate([video * g for g in gains])[:max(world, video.shape[0])]
+        spec = np.concatenate([spec * g for g in gains])[:video.shape[0]]
+        labels = np.concatenate([labels] * reps)[:video.shape[0]]
+        keep = video.shape[0] // world * world
+        video, spec, labels = video[:keep], spec[:keep], labels[:keep]
     B = video.shape[0]
     hc, K = 3, 309
 
