@@ -208,6 +208,68 @@ __global__ void bn_bwd_reduce_kernel(const float4* __restrict__ g, const float4*
     }
 }
 
+// Same sums for narrow tensors (c4n <= 128 float4 per row): the block is R complete rows wide (R * c4n threads, thread t
+// owns channel group t % c4n of row slot t / c4n), so every lane is busy and consecutive threads read consecutive
+// addresses across row boundaries.  The 32-lanes-per-row mapping above leaves 4 of 32 lanes active on the second
+// column block of a 144-channel tensor (c4n = 36) and half of them on a 64-channel one.
+__global__ void bn_bwd_reduce_rows_kernel(const float4* __restrict__ g, const float4* __restrict__ z,
+                                          const float4* __restrict__ act, int mask_mode, const float4* __restrict__ scale,
+                                          const float4* __restrict__ shift, const float4* __restrict__ mean,
+                                          const float4* __restrict__ invstd, long long M, int c4n, int R,
+                                          float* __restrict__ partial /*[gridDim.x][2][c4n*4]*/) {
+    extern __shared__ float4 red_rows[];   // [2][R][c4n]
+    const int t = threadIdx.x;
+    const int rs = t / c4n, c4 = t - rs * c4n;
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+    const float4 mu = __ldg(mean + c4), is = __ldg(invstd + c4);
+    float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
+    if (mask_mode == 2) {
+        sc = __ldg(scale + c4);
+        sh = __ldg(shift + c4);
+    }
+    const long long rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > M) r1 = M;
+    for (long long r = r0 + rs; r < r1; r += 4 * R) {   // 4 row groups per iteration: 8-12 independent 16-byte loads in flight
+        float4 zz[4], gg[4], aa[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long rr = r + (long long)R * u;
+            const bool ok = rr < r1;
+            const size_t i = (size_t)(ok ? rr : r) * c4n + c4;
+            zz[u] = z[i];
+            gg[u] = g[i];
+            aa[u] = (mask_mode == 1) ? act[i] : zz[u];
+            if (!ok) gg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float4 a = aa[u];
+            if (mask_mode == 2) a = affine4(zz[u], sc, sh);
+            const float4 gm = masked_g(gg[u], mask_mode, a);
+            s1.x += gm.x; s1.y += gm.y; s1.z += gm.z; s1.w += gm.w;
+            s2.x = fmaf(gm.x, (zz[u].x - mu.x) * is.x, s2.x);
+            s2.y = fmaf(gm.y, (zz[u].y - mu.y) * is.y, s2.y);
+            s2.z = fmaf(gm.z, (zz[u].z - mu.z) * is.z, s2.z);
+            s2.w = fmaf(gm.w, (zz[u].w - mu.w) * is.w, s2.w);
+        }
+    }
+    red_rows[t] = s1;
+    red_rows[R * c4n + t] = s2;
+    __syncthreads();
+    if (t < 2 * c4n) {
+        const int which = t / c4n, c = t - which * c4n;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < R; ++k) {
+            const float4 v = red_rows[(which * R + k) * c4n + c];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float* dst = partial + ((size_t)blockIdx.x * 2 + which) * (c4n * 4) + c * 4;
+        *reinterpret_cast<float4*>(dst) = acc;
+    }
+}
+
 // dz = scale * (g - sum_g/count - zhat * sum_gz/count);   optional gres (+)= g (masked) for the residual branch
 __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* __restrict__ z,
                                     const float4* __restrict__ act, int mask_mode, const float4* __restrict__ scale,
@@ -504,10 +566,17 @@ extern "C" int selavi_bn_bwd_reduce(const float* g, const float* z, const float*
     if (mask_mode == 2 && (!scale || !shift)) return selavi_fail(-1, "bn_bwd_reduce: mask_mode 2 needs scale/shift");
     const int c4n = cs / 4;
     const int nblk = selavi_bn_bwd_blocks(M);
-    dim3 grid(nblk, (c4n + 31) / 32);
-    bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)g, (const float4*)z, (const float4*)act,
-                                                                 mask_mode, (const float4*)scale, (const float4*)shift,
-                                                                 (const float4*)mean, (const float4*)invstd, M, c4n, partial);
+    if (c4n <= 128 && c4n % 32 != 0) {
+        const int R = 256 / c4n;   // >= 2 complete rows per block; 2 * c4n <= R * c4n threads for the final sum
+        bn_bwd_reduce_rows_kernel<<<nblk, R * c4n, (size_t)2 * R * c4n * sizeof(float4), (cudaStream_t)stream>>>(
+            (const float4*)g, (const float4*)z, (const float4*)act, mask_mode, (const float4*)scale, (const float4*)shift,
+            (const float4*)mean, (const float4*)invstd, M, c4n, R, partial);
+    } else {
+        dim3 grid(nblk, (c4n + 31) / 32);
+        bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)g, (const float4*)z, (const float4*)act,
+                                                                     mask_mode, (const float4*)scale, (const float4*)shift,
+                                                                     (const float4*)mean, (const float4*)invstd, M, c4n, partial);
+    }
     LAUNCH_CHECK("bn_bwd_reduce");
     return selavi_bn_reduce_partials(partial, nblk, cs, cs, sums, stream);
 }
