@@ -294,8 +294,20 @@ class AVModel(nn.Module):
         return [getattr(self, "%s%d" % (prefix, h)) for h in range(self.hc)]
 
     def forward(self, img, spec, whichhead=0):
-        img_features = self.video_network(img).squeeze()
-        aud_features = self.audio_network(spec).squeeze()
+        if engine.AUDIO_STREAM and img.is_cuda and spec.is_cuda and img.device == spec.device:
+            # the small audio tower overlaps the video tower on a second stream (its backward follows it there)
+            main = torch.cuda.current_stream(img.device)
+            side = engine.audio_stream(img.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                aud_features = self.audio_network(spec).squeeze()
+            img_features = self.video_network(img).squeeze()
+            main.wait_stream(side)
+            spec.record_stream(side)
+            aud_features.record_stream(main)
+        else:
+            img_features = self.video_network(img).squeeze()
+            aud_features = self.audio_network(spec).squeeze()
         if self.return_features:
             return img_features, aud_features
         if len(aud_features.shape) == 1:
