@@ -626,8 +626,20 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int slice
             row = (size_t)(taps - 1 - tap) * rs + o;
             col = c;
         }
-        float s = 0.f;
-        for (int k = 0; k < slices; ++k) s += partial[((size_t)k * mg_pad + row) * ntot + col];
+        // four independent partial chains (fixed association: still bit-reproducible) keep 4 loads in flight per thread;
+        // with up to ~450 split-K slices a single dependent chain made this kernel latency bound
+        const float* src = partial + row * ntot + col;
+        const size_t kstride = (size_t)mg_pad * ntot;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int k = 0;
+        for (; k + 4 <= slices; k += 4) {
+            s0 += src[(size_t)k * kstride];
+            s1 += src[(size_t)(k + 1) * kstride];
+            s2 += src[(size_t)(k + 2) * kstride];
+            s3 += src[(size_t)(k + 3) * kstride];
+        }
+        for (; k < slices; ++k) s0 += src[(size_t)k * kstride];
+        const float s = (s0 + s1) + (s2 + s3);
         float* dst = dW + ((size_t)o * ci + c) * taps + tap;
         *dst = accumulate ? (*dst + s) : s;
     }
