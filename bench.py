@@ -266,9 +266,10 @@ def run_ours(args):
     from selavi_b200 import engine
     ops.PROFILE = []
     side, engine.WGRAD_STREAM = engine.WGRAD_STREAM, False   # per-kernel times: no concurrent weight-gradient stream
+    aud, engine.AUDIO_STREAM = engine.AUDIO_STREAM, False    # ... and no concurrent audio-tower stream
     train_step(video_d, spec_d, labels_d)
     torch.cuda.synchronize()
-    engine.WGRAD_STREAM = side
+    engine.WGRAD_STREAM, engine.AUDIO_STREAM = side, aud
     prof, ops.PROFILE = ops.PROFILE, None
     agg = {}
     if os.environ.get("SELAVI_BENCH_DETAIL") and rank == 0:
