@@ -58,6 +58,9 @@ def main():
         video = (r.standard_normal((n,) + video.shape[1:]).astype(np.float32) * gains.reshape(n, 1, 1, 1, 1))
         spec = ((r.standard_normal((n,) + spec.shape[1:]) * 17.89 + 1.93).astype(np.float32) * gains.reshape(n, 1, 1, 1))
         labels = r.integers(0, 309, (n,) + labels.shape[1:]).astype(labels.dtype)
+    if os.environ.get("MGPU_CLIPS"):   # experiment: fewer clips (e.g. one per rank)
+        k = int(os.environ["MGPU_CLIPS"])
+        video, spec, labels = video[:k], spec[:k], labels[:k]
     B = video.shape[0]
     hc, K = 3, 309
 
@@ -92,6 +95,11 @@ def main():
         if e > worst:
             worst, worst_name = e, n
     print(f"[rank {rank}] DDP+SyncBN vs single GPU: loss {float(l_ddp):.6f} vs {float(l_single):.6f}, worst grad rel err {worst:.2e} ({worst_name})", flush=True)
+    if rank == 0:
+        errs = sorted(((float((p.grad - g_single[n]).norm() / (g_single[n].norm() + 1e-12)), n, float(g_single[n].norm()))
+                       for n, p in ddp_m.named_parameters()), reverse=True)[:6]
+        for e, n, gn in errs:
+            print(f"    {e:.2e}  |g|={gn:.3e}  {n}", flush=True)
     ok &= abs(float(l_ddp) - float(l_single)) < 1e-4 * abs(float(l_single)) and worst < 5e-3
     # ---- 3. row-sharded dataset sweep + label assignment (get_cluster_assignments_gpu) == single-GPU result
     from selavi_b200.sk_utils import get_cluster_assignments_gpu
