@@ -87,6 +87,7 @@ SIGNATURES = {
     "selavi_sgd_step_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_int, c_void_p]),
     "selavi_mel_logfbank": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p, c_int, c_int, c_double, c_int,
                                     c_void_p, c_void_p]),
+    "selavi_conv_wgrad_plan": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "selavi_clip_augment": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "selavi_debug_umma_probe": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.c_ulonglong, ctypes.c_ulonglong,
                                         ctypes.c_uint, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -691,6 +691,35 @@ WgPlan wg_plan(int co, int taps, int cs, long long M, bool bf16) {
     return pl;
 }
 
+// Tiling + operand orientation of one weight gradient (host logic, also exported as selavi_conv_wgrad_plan).
+// Exchanged operands (bf16 kernel, stride-1 "same" convolutions): sum_px dz[px][co] x[px+tap][ci] = sum_q
+// dz[q-tap][co] x[q][ci], i.e. the same kernel with dz as the tap-shifted row operand (rows = (flipped tap, co)) and
+// x as the column operand (N = ci).  Pays when that gives fewer / better-shaped MMAs: one M=128 MMA costs about
+// max(N/2 + 12, 59) clocks (tools/umma_rate.cu), so the 144->64 temporal convs of layer 1 run as 2 row tiles x N=144
+// instead of 4 row tiles x N=64.
+WgPlan wg_choose(const int* geom, int ci_real, bool bf16, bool* swapped) {
+    const int ts = geom[2], hs = geom[3], ws = geom[4], cs = geom[5], td = geom[6], hd = geom[7], wd = geom[8], cd = geom[9];
+    const int kt = geom[10], kh = geom[11], kw = geom[12], st = geom[13], sh = geom[14], sw = geom[15];
+    const int pt = geom[16], ph = geom[17], pw = geom[18], co = geom[19];
+    const long long M = (long long)geom[1] * td * hd * wd;
+    const int taps = kt * kh * kw;
+    WgPlan pl = wg_plan(co, taps, cs, M, bf16);
+    *swapped = false;
+    if (bf16 && st == 1 && sh == 1 && sw == 1 && ts == td && hs == hd && ws == wd && 2 * pt == kt - 1 && 2 * ph == kh - 1 &&
+        2 * pw == kw - 1 && !getenv("SELAVI_WGRAD_NOSWAP")) {
+        const WgPlan ps = wg_plan(ci_real, taps, cd, M, true);
+        auto cost = [](const WgPlan& w) {
+            const double t = w.bnt / 2.0 + 12.0;
+            return (double)w.mtiles * w.ntiles * (t < 59.0 ? 59.0 : t);
+        };
+        if (cost(ps) < 0.9 * cost(pl)) {
+            *swapped = true;
+            pl = ps;
+        }
+    }
+    return pl;
+}
+
 }  // namespace
 
 namespace {
@@ -747,25 +776,8 @@ int wgrad_run(const float* src, const float* dz, const void* z_hi_in, const void
     p.M = (int)M;
     const int taps = p.kt * p.kh * p.kw;
     const bool bf16 = passes < 10;
-    WgPlan pl = wg_plan(co, taps, p.cs, M, bf16);
-    // Exchanged operands (bf16 kernel, stride-1 "same" convolutions): sum_px dz[px][co] x[px+tap][ci] = sum_q
-    // dz[q-tap][co] x[q][ci], i.e. the same kernel with dz as the tap-shifted row operand (rows = (flipped tap, co)) and
-    // x as the column operand (N = ci).  Pays when that gives fewer / better-shaped MMAs: one M=128 MMA costs about
-    // max(N/2 + 12, 59) clocks (tools/umma_rate.cu), so the 144->64 temporal convs of layer 1 run as 2 row tiles x N=144
-    // instead of 4 row tiles x N=64.
     bool swapped = false;
-    if (bf16 && p.st == 1 && p.sh == 1 && p.sw == 1 && p.ts == p.td && p.hs == p.hd && p.ws == p.wd &&
-        2 * p.pt == p.kt - 1 && 2 * p.ph == p.kh - 1 && 2 * p.pw == p.kw - 1 && !getenv("SELAVI_WGRAD_NOSWAP")) {
-        const WgPlan ps = wg_plan(ci_real, taps, p.cd, M, true);
-        auto cost = [](const WgPlan& w) {
-            const double t = w.bnt / 2.0 + 12.0;
-            return (double)w.mtiles * w.ntiles * (t < 59.0 ? 59.0 : t);
-        };
-        if (cost(ps) < 0.9 * cost(pl)) {
-            swapped = true;
-            pl = ps;
-        }
-    }
+    const WgPlan pl = wg_choose(geom, ci_real, bf16, &swapped);
     p.mtiles = pl.mtiles; p.bnt = pl.bnt; p.ntiles = pl.ntiles; p.natom = pl.natom;
     p.total_kstages = pl.total_kstages; p.kstages_per_slice = pl.kstages_per_slice;
     p.pro_relu = pro_relu;
@@ -836,6 +848,22 @@ int wgrad_run(const float* src, const float* dz, const void* z_hi_in, const void
 }
 
 }  // namespace
+
+// host-only query: tiling of the bf16x3 weight gradient for this geometry (row tiles, column tile width, column tiles,
+// row tiles per CTA, split-K slices, and whether the operands are exchanged)
+extern "C" int selavi_conv_wgrad_plan(const int* geom, int ci_real, int* mtiles, int* bnt, int* ntiles, int* tiles_per_cta,
+                                      int* slices, int* exchanged) {
+    if (!geom || ci_real <= 0) return selavi_fail(-1, "conv_wgrad_plan: bad arguments");
+    bool sw = false;
+    const WgPlan pl = wg_choose(geom, ci_real, true, &sw);
+    if (mtiles) *mtiles = pl.mtiles;
+    if (bnt) *bnt = pl.bnt;
+    if (ntiles) *ntiles = pl.ntiles;
+    if (tiles_per_cta) *tiles_per_cta = pl.G;
+    if (slices) *slices = pl.slices;
+    if (exchanged) *exchanged = sw ? 1 : 0;
+    return 0;
+}
 
 // geom: same 20 ints as selavi_conv_gemm with mode 0 (the FORWARD geometry of the convolution); dz is [M, cd].
 extern "C" int selavi_conv_wgrad(const float* src, const float* dz, float* dW, const int* geom, int ci_real,

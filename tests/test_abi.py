@@ -48,3 +48,32 @@ def test_argument_validation_without_gpu(built_lib):
     code = built_lib.selavi_sk_solve(None, 0, 0, 309, 20.0, 0, None, None, None, None, None, 10, 10, 0.1, 1, 1, 1, None,
                                      None, None, 1, 0, None, None, None)
     assert code < 0 and b"sk" in built_lib.selavi_last_error()
+
+
+def test_wgrad_plan_host_logic(built_lib):
+    """Weight-gradient tiling / operand orientation (csrc/wgrad.cu:wg_choose) at configs[1] shapes: groups of row tiles
+    that share a dz stage are bounded by TMEM (G * bnt <= 512 columns) and by 3 pipeline stages of shared memory; the
+    operands are exchanged only for stride-1 'same' convs where the MMA cost model says so."""
+    import ctypes
+    from selavi_b200 import ops
+
+    def plan(nb, ci, co, thw, k, s, p):
+        v = [ctypes.c_int() for _ in range(6)]
+        assert built_lib.selavi_conv_wgrad_plan(ops.ConvGeom(nb, ci, co, thw, k, s, p).arr(0), ci, *[ctypes.byref(x) for x in v]) == 0
+        return dict(zip(("mtiles", "bnt", "ntiles", "G", "slices", "exchanged"), (x.value for x in v)))
+
+    l1s = plan(16, 64, 144, (32, 56, 56), (1, 3, 3), (1, 1, 1), (0, 1, 1))
+    assert (l1s["mtiles"], l1s["bnt"], l1s["ntiles"], l1s["G"], l1s["exchanged"]) == (5, 144, 1, 3, 0)
+    l1t = plan(16, 144, 64, (32, 56, 56), (3, 1, 1), (1, 1, 1), (1, 0, 0))      # 4 row tiles x N=64 -> 2 row tiles x N=144
+    assert (l1t["mtiles"], l1t["bnt"], l1t["G"], l1t["exchanged"]) == (2, 144, 2, 1)
+    strided = plan(16, 64, 230, (32, 56, 56), (1, 3, 3), (1, 2, 2), (0, 1, 1))  # strided: never exchanged
+    assert strided["exchanged"] == 0 and strided["bnt"] == 240
+    for name, cfg in {"l2s": (16, 128, 288, (16, 28, 28), (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+                      "l4s": (16, 512, 1152, (4, 7, 7), (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+                      "l4t": (16, 1152, 512, (4, 7, 7), (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+                      "stem_t": (16, 45, 64, (32, 56, 56), (3, 1, 1), (1, 1, 1), (1, 0, 0))}.items():
+        pl = plan(*cfg)
+        assert 1 <= pl["G"] <= 3 and pl["G"] * pl["bnt"] <= 512, name
+        assert pl["bnt"] % 16 == 0 and pl["bnt"] <= 256 and pl["slices"] >= 1, name
+        groups = -(-pl["mtiles"] // pl["G"])
+        assert groups * pl["ntiles"] * pl["slices"] <= 148 * 3 + groups * pl["ntiles"], name   # at most ~3 waves of CTAs
