@@ -77,3 +77,32 @@ def test_wgrad_plan_host_logic(built_lib):
         assert pl["bnt"] % 16 == 0 and pl["bnt"] <= 256 and pl["slices"] >= 1, name
         groups = -(-pl["mtiles"] // pl["G"])
         assert groups * pl["ntiles"] * pl["slices"] <= 148 * 3 + groups * pl["ntiles"], name   # at most ~3 waves of CTAs
+
+
+def test_halo_plan_host_logic(built_lib):
+    """Tiling of the tap-reuse kernel (csrc/conv_halo.cu:hl_plan, host only): 128-pixel tiles (8 frames x 16 positions for
+    3x1x1, 128 positions of the row-padded frame for 1x3x3), column tiles of <= 256 channels in multiples of 16, packed
+    weights = tiles x chunks x taps x (hi|lo) x bnt x 128 B; strided / other kernels are refused (return 1)."""
+    import ctypes
+    from selavi_b200 import ops
+
+    def plan(nb, ci, co, thw, k, s=(1, 1, 1), mode=0):
+        p = (1, 0, 0) if k[0] == 3 else ((0, 1, 1) if k[1] == 3 else (0, 0, 0))
+        mt, bnt, nt, wb = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
+        code = built_lib.selavi_conv_halo_plan(ops.ConvGeom(nb, ci, co, thw, k, s, p).arr(mode), ctypes.byref(mt), ctypes.byref(bnt),
+                                               ctypes.byref(nt), ctypes.byref(wb))
+        return code, (mt.value, bnt.value, nt.value, wb.value)
+
+    assert plan(16, 144, 64, (32, 56, 56), (3, 1, 1)) == (0, (16 * 4 * 196, 64, 1, 3 * 3 * 2 * 64 * 128))
+    assert plan(16, 64, 144, (32, 56, 56), (1, 3, 3)) == (0, (16 * 32 * 26, 144, 1, 1 * 9 * 2 * 144 * 128))
+    # 230 channels: one 240-wide column tile would leave room for a single 61 KB weight slot next to the two 48 KB windows
+    # and the staging tiles, so the plan falls back to two 128-wide column tiles
+    assert plan(16, 128, 230, (16, 28, 28), (1, 3, 3)) == (0, (1792, 128, 2, 2 * 2 * 9 * 2 * 128 * 128))
+    assert plan(16, 128, 288, (16, 28, 28), (1, 3, 3)) == (0, (1792, 144, 2, 2 * 2 * 9 * 2 * 144 * 128))
+    assert plan(16, 512, 1152, (4, 7, 7), (1, 3, 3)) == (0, (64, 192, 6, 6 * 8 * 9 * 2 * 192 * 128))
+    # data-gradient mode of the same stride-1 convs: source / destination channels exchanged
+    code, (mt, bnt, nt, _) = plan(16, 64, 144, (32, 56, 56), (1, 3, 3), mode=1)
+    assert code == 0 and (mt, bnt, nt) == (16 * 32 * 26, 64, 1)
+    for cfg in [(16, 64, 230, (32, 56, 56), (1, 3, 3), (1, 2, 2)), (16, 230, 128, (32, 28, 28), (3, 1, 1), (2, 1, 1)),
+                (16, 64, 128, (32, 56, 56), (1, 1, 1), (2, 2, 2))]:
+        assert plan(*cfg)[0] == 1
