@@ -43,6 +43,13 @@ const char* selavi_last_error(void);
  */
 /* PS[n,k] = softmax_f64(logits_v[n,:])[k] * softmax_f64(logits_a[n,:])[k]  (src/sk_utils.py:206-211,309-315) */
 int selavi_sk_softmax_product(const float* logits_v, const float* logits_a, long long n, int K, double* PS, void* stream);
+/* out[n,k] = softmax_f64(logits[n,:])[k]  (torch.nn.functional.softmax(x, dim=1, dtype=torch.float64), src/sk_utils.py:272-275) */
+int selavi_sk_softmax64(const float* logits, long long n, int K, double* out, void* stream);
+/* C[i,j] = sum_n |P1[n,i] - P2[n,j]|, float64 [K,K]: every value of the cost function c(a, b) that the head-alignment
+ * search `match_order` evaluates (src/sk_utils.py:430-447), computed once; P1, P2 [n,K] float64 row-major.  `workspace`
+ * holds selavi_l1_cost_workspace_bytes(n, K) bytes of split-N partial tiles (summed in a fixed order: bit-reproducible). */
+size_t selavi_l1_cost_workspace_bytes(long long n, int K);
+int selavi_l1_cost_matrix(const double* P1, const double* P2, long long n, int K, double* C, void* workspace, void* stream);
 size_t selavi_sk_workspace_bytes(int K);
 int selavi_sk_kp(int K);
 int selavi_sk_solve(double* PS, long long n_local, long long n_global, int K, double lamb, int use_dist,
@@ -239,15 +246,6 @@ int selavi_symm_memset(void* ptr, int value, size_t bytes, void* stream);
  * (strictly increasing, > 0). */
 int selavi_p2p_allreduce_f64(double* data, int n, int world, int rank, void* const* peer_recv, void* const* peer_flag,
                              long long slot_off, int flag_idx, long long seqval, void* stream);
-
-/* ------------------------------------------------------------------------------------------------
- * Diagnostics: issue n_mma tcgen05.mma instructions (kind 0 = tf32, 1 = f16/bf16) on host-provided raw shared-memory operand
- * images / descriptor bits and dump the 128 x N fp32 accumulator (tools/umma_probe.py).
- */
-int selavi_debug_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
-                            unsigned long long adesc_base, unsigned long long bdesc_base, unsigned idesc, int n_mma,
-                            const unsigned* a_offs, const unsigned* b_offs, int N, int kind, float* out,
-                            void* stream);
 
 #ifdef __cplusplus
 }

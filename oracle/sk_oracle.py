@@ -112,3 +112,48 @@ def match_order_oracle(emb1, emb2_in, steps=50000, restarts=2):
             best_cost = cost_try
             fin_perm = perm.copy()
     return fin_perm
+
+
+def softmax64(x):
+    """torch.nn.functional.softmax(x, dim=1, dtype=torch.float64) (src/sk_utils.py:206-211,272-275)."""
+    x = np.asarray(x, dtype=np.float64)
+    e = np.exp(x - x.max(1, keepdims=True))
+    return e / e.sum(1, keepdims=True)
+
+
+def cluster_assignments_oracle(logits_v, logits_a, N, world_size, ind_groups, match_first_iter, kdists=None, lamb=20.0):
+    """CPU restatement of the BOOKKEEPING of `get_cluster_assignments_gpu` (src/sk_utils.py:183-327) for inputs that do
+    not depend on the sweep order: `logits_v[h]`, `logits_a[h]` are the outputs of head h ([N, K], dataset-index order;
+    for headcount 1 the model's own outputs).  Follows the reference's control flow and np.random consumption:
+
+      order_heads = shuffle(range(hc))                                            (:183-184)
+      for g in range(ind_groups):                                                 (:186)
+          [sweep]                                                                 (:188-254)
+          if match and iter_num == 0: for head in order_heads[g::ind_groups]:     (:257-286)
+              perm = match_order(softmax64(v), softmax64(a)); permute the audio head's last Linear rows
+              (= the COLUMNS of its output from now on)                           (:424-467)
+          for head in order_heads[g::ind_groups]:                                 (:300-323)
+              PS = softmax64(v) * softmax64(a); cost, L_head = SK(PS); L[indices, head] = L_head
+
+    Rows `>= (N // world_size) * world_size` are never visited and keep label 0 (:157-161).
+    Returns (L [N, hc] int64, perms {head: permutation}, order_heads)."""
+    hc = len(logits_v)
+    order_heads = list(range(hc))
+    np.random.shuffle(order_heads)
+    visited = (N // world_size) * world_size
+    L = np.zeros((N, hc), dtype=np.int64)
+    perms = {}
+    la = [np.asarray(a, dtype=np.float32).copy() for a in logits_a]
+    for g in range(ind_groups):
+        heads = order_heads[g::ind_groups]
+        if match_first_iter:
+            for head in heads:
+                perm = match_order_oracle(softmax64(logits_v[head][:visited]), softmax64(la[head][:visited]))
+                if hc > 1:          # multi-head: head_a.forward(PS_a) is re-evaluated after the permutation (:309-312);
+                    la[head] = la[head][:, perm]   # headcount 1 keeps using the outputs gathered BEFORE it (:301-303)
+                perms[head] = perm
+        for head in heads:
+            PS = softmax64(logits_v[head][:visited]) * softmax64(la[head][:visited])
+            out = optimize_L_sk(PS, lamb=lamb, kdist=None if kdists is None else kdists[head])
+            L[:visited, head] = out["labels"]
+    return L, perms, order_heads

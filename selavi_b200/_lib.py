@@ -23,6 +23,9 @@ SIGNATURES = {
     "selavi_version": (c_int, []),
     "selavi_last_error": (ctypes.c_char_p, []),
     "selavi_sk_softmax_product": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
+    "selavi_sk_softmax64": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_void_p]),
+    "selavi_l1_cost_workspace_bytes": (c_size_t, [c_ll, c_int]),
+    "selavi_l1_cost_matrix": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p]),
     "selavi_sk_workspace_bytes": (c_size_t, [c_int]),
     "selavi_sk_kp": (c_int, [c_int]),
     "selavi_sk_solve": (c_int, [c_void_p, c_ll, c_ll, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -89,8 +92,6 @@ SIGNATURES = {
                                     c_void_p, c_void_p]),
     "selavi_conv_wgrad_plan": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "selavi_clip_augment": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "selavi_debug_umma_probe": (c_int, [c_void_p, c_int, c_void_p, c_int, ctypes.c_ulonglong, ctypes.c_ulonglong,
-                                        ctypes.c_uint, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "selavi_symm_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
     "selavi_symm_open": (c_int, [c_void_p, c_void_p]),
     "selavi_symm_close": (c_int, [c_void_p]),
@@ -106,14 +107,14 @@ class SelaviError(RuntimeError):
 
 # kernels launched per C-ABI call (for bench.py's `gpu_launches` claim); host-only queries launch none
 KERNELS_PER_CALL = {
-    "selavi_sk_solve": 1, "selavi_sk_softmax_product": 1, "selavi_conv_pack_weights": 1, "selavi_conv_gemm": 1, "selavi_conv_wgrad": 4,
+    "selavi_sk_solve": 1, "selavi_sk_softmax_product": 1, "selavi_sk_softmax64": 1, "selavi_l1_cost_matrix": 2, "selavi_conv_pack_weights": 1, "selavi_conv_gemm": 1, "selavi_conv_wgrad": 4,
     "selavi_bn_reduce_partials": 1, "selavi_bn_finalize": 1, "selavi_bn_eval_affine": 1, "selavi_bn_apply": 1,
     "selavi_bn_bwd_reduce": 2, "selavi_bn_bwd_apply": 1, "selavi_relu_bwd": 1, "selavi_maxpool3x3s2_fwd": 1,
     "selavi_maxpool3x3s2_bwd": 1, "selavi_avgpool_fwd": 1, "selavi_avgpool_bwd": 1, "selavi_nchw_to_cl": 1,
     "selavi_sgd_step": 1, "selavi_sgd_step_host": 6, "selavi_bgemm": 1, "selavi_heads_bn_stats": 1, "selavi_heads_bn_finalize": 1,
     "selavi_heads_bn_eval_affine": 1, "selavi_heads_act": 1, "selavi_heads_bn_bwd_reduce": 1,
     "selavi_heads_bn_bwd_apply": 1, "selavi_heads_sum_masked": 1, "selavi_heads_colsum": 1, "selavi_ce_loss": 2,
-    "selavi_debug_umma_probe": 1, "selavi_mel_logfbank": 1, "selavi_split_bf16": 1, "selavi_p2p_allreduce_f64": 1, "selavi_conv_wgrad_bf16": 3,
+    "selavi_mel_logfbank": 1, "selavi_split_bf16": 1, "selavi_p2p_allreduce_f64": 1, "selavi_conv_wgrad_bf16": 3,
     "selavi_dgrad_pack_weights": 1, "selavi_conv_dgrad_bf16": 1,
     "selavi_conv_halo_pack_weights": 1, "selavi_conv_halo_fwd": 1, "selavi_conv_halo_dgrad": 1, "selavi_clip_augment": 1,
 }

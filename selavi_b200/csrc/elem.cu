@@ -9,6 +9,9 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include <mutex>
+#include <vector>
+
 #include "../../include/selavi_b200.h"
 #include "common.cuh"
 
@@ -493,27 +496,56 @@ __global__ void sgd_chunk_kernel(const SgdChunk c, int n_tensors, float lr, floa
 #define LAUNCH_CHECK(what) SV_CUDA_CHECK(cudaGetLastError(), what)
 
 namespace {
-// per-device scratch of the chunked reduction (stream-ordered use only: one reduction in flight per device)
-double* g_rp_scratch[16] = {nullptr};
-unsigned* g_rp_tickets[16] = {nullptr};
+// Scratch of the chunked reduction, one per (device, stream): launches on ONE stream are ordered, so a reduction owns its
+// stream's scratch until it completes; reductions on different streams (the audio tower and the weight-gradient side
+// streams run next to the video tower) never share chunk slots or tickets.
+struct RpScratch {
+    int dev;
+    cudaStream_t stream;
+    double* scratch;
+    unsigned* tickets;
+};
+std::mutex g_rp_mutex;
+std::vector<RpScratch> g_rp_table;
+
+int rp_scratch_for(int dev, cudaStream_t stream, double** scratch, unsigned** tickets) {
+    std::lock_guard<std::mutex> lock(g_rp_mutex);
+    for (const RpScratch& e : g_rp_table) {
+        if (e.dev == dev && e.stream == stream) {
+            *scratch = e.scratch;
+            *tickets = e.tickets;
+            return 0;
+        }
+    }
+    RpScratch e{dev, stream, nullptr, nullptr};
+    const size_t tbytes = sizeof(unsigned) * 2 * (RP_MAX_CS / 32);
+    SV_CUDA_CHECK(cudaMalloc(&e.scratch, sizeof(double) * RP_MAX_CHUNKS * 2 * RP_MAX_CS), "bn_reduce_partials: scratch");
+    SV_CUDA_CHECK(cudaMalloc(&e.tickets, tbytes), "bn_reduce_partials: tickets");
+    // cudaMalloc/cudaMemset on the legacy default stream complete before this call returns to the (stream-ordered) caller
+    SV_CUDA_CHECK(cudaMemset(e.tickets, 0, tbytes), "bn_reduce_partials: tickets");
+    SV_CUDA_CHECK(cudaDeviceSynchronize(), "bn_reduce_partials: tickets");
+    g_rp_table.push_back(e);
+    *scratch = e.scratch;
+    *tickets = e.tickets;
+    return 0;
 }
+}  // namespace
 
 extern "C" int selavi_bn_reduce_partials(const float* partial, int tiles, int ctot, int cs, double* sums, void* stream) {
     if (!partial || !sums || tiles <= 0 || cs <= 0 || cs > RP_MAX_CS) return selavi_fail(-1, "bn_reduce_partials: bad arguments");
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 16) return selavi_fail(-1, "bn_reduce_partials: device index out of range");
-    if (!g_rp_scratch[dev]) {
-        SV_CUDA_CHECK(cudaMalloc(&g_rp_scratch[dev], sizeof(double) * RP_MAX_CHUNKS * 2 * RP_MAX_CS), "bn_reduce_partials: scratch");
-        SV_CUDA_CHECK(cudaMalloc(&g_rp_tickets[dev], sizeof(unsigned) * 2 * (RP_MAX_CS / 32)), "bn_reduce_partials: tickets");
-        SV_CUDA_CHECK(cudaMemset(g_rp_tickets[dev], 0, sizeof(unsigned) * 2 * (RP_MAX_CS / 32)), "bn_reduce_partials: tickets");
-    }
     int nchunk = tiles / 256;
     if (nchunk < 1) nchunk = 1;
     if (nchunk > RP_MAX_CHUNKS) nchunk = RP_MAX_CHUNKS;
+    double* scratch = nullptr;
+    unsigned* tickets = nullptr;
+    if (nchunk > 1) {
+        int dev = 0;
+        SV_CUDA_CHECK(cudaGetDevice(&dev), "bn_reduce_partials: cudaGetDevice");
+        const int rc = rp_scratch_for(dev, (cudaStream_t)stream, &scratch, &tickets);
+        if (rc) return rc;
+    }
     dim3 grid((cs + 31) / 32, 2, nchunk), block(32, 32);
-    bn_reduce_partials_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(partial, tiles, ctot, cs, sums, g_rp_scratch[dev],
-                                                                        g_rp_tickets[dev]);
+    bn_reduce_partials_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(partial, tiles, ctot, cs, sums, scratch, tickets);
     LAUNCH_CHECK("bn_reduce_partials");
     return 0;
 }

@@ -216,11 +216,16 @@ __global__ void ce_kernel(const void* const* logit_tbl, const float* __restrict_
     for (int w = 0; w < nw; ++w) s += red[w];
     const long long lab = labels[(size_t)b * lab_sb + (size_t)h * lab_sh];
     const float lse = logf(s) + mx;
-    if (tid == 0) loss[(size_t)h * B + b] = (lab >= 0 && lab < K) ? lse - x[lab] : 0.f;
+    // A label outside [0, K) is a corrupt / uninitialised pseudo-label (torch.nn.functional.cross_entropy raises a device
+    // assert for it): poison the loss row and its gradient row with NaN so that the step fails loudly instead of
+    // training on softmax-only gradients.
+    const bool lab_ok = lab >= 0 && lab < K;
+    if (tid == 0) loss[(size_t)h * B + b] = lab_ok ? lse - x[lab] : __int_as_float(0x7fc00000);
     if (dlogits) {
         float* d = dlogits + ((size_t)h * B + b) * K;
         const float inv = 1.f / s;
-        for (int k = tid; k < K; k += blockDim.x) d[k] = (expf(x[k] - mx) * inv - (k == lab ? 1.f : 0.f)) * gscale;
+        for (int k = tid; k < K; k += blockDim.x)
+            d[k] = lab_ok ? (expf(x[k] - mx) * inv - (k == lab ? 1.f : 0.f)) * gscale : __int_as_float(0x7fc00000);
     }
 }
 

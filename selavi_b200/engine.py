@@ -82,7 +82,12 @@ def _allreduce(t, bn):
             from .symm import P2PAllReduce
             try:
                 ar = P2PAllReduce(group)
-            except _lib.SelaviError:
+            except _lib.SelaviError as e:
+                # P2PAllReduce / SymmetricBuffer agree on availability collectively: this branch is taken by EVERY rank
+                # of the group or by none, so the NCCL fallback below cannot be mixed with spinning P2P kernels
+                import warnings
+                warnings.warn(f"selavi_b200: NVSwitch P2P exchange of the SyncBatchNorm statistics unavailable ({e}); "
+                              "falling back to torch.distributed.all_reduce (NCCL)")
                 ar = False
             _p2p[key] = ar
         if ar:

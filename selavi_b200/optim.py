@@ -1,7 +1,7 @@
 """Fused multi-tensor SGD (momentum + weight decay) — one kernel launch for all 247 parameter tensors.
 
 Same update rule and constructor as `torch.optim.SGD(params, lr, momentum, weight_decay)` used at
-main.py:132-137 (dampening 0, no nesterov): d = g + wd*p; buf = d on the first step else mu*buf + d; p -= lr*buf.
+main.py:132-137 (dampening 0, no nesterov): d = g + wd*p; buf = mu*buf + d (buf starts at zero, i.e. buf = d on a parameter's first step); p -= lr*buf.
 `state_dict()` uses torch's layout (`momentum_buffer` per parameter), so checkpoints are interchangeable.
 """
 import ctypes
@@ -29,12 +29,13 @@ class SGD(torch.optim.Optimizer):
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
                 continue
-            first = False
+            # a missing momentum buffer is created as zeros: mu*0 + d == d is torch's first-step rule, per parameter
+            # (a per-group "first step" flag would reset the momentum of every other tensor when one parameter
+            # receives its first gradient late: find_unused_parameters, add_param_group, partially loaded state)
             for p in ps:
                 st = self.state[p]
                 if "momentum_buffer" not in st or st["momentum_buffer"] is None:
                     st["momentum_buffer"] = torch.zeros_like(p)
-                    first = True
                 if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()):
                     raise ValueError("selavi_b200.optim.SGD needs contiguous fp32 CUDA parameters and gradients")
             n = len(ps)
@@ -45,7 +46,7 @@ class SGD(torch.optim.Optimizer):
             sizes = (ctypes.c_longlong * n)(*[p.numel() for p in ps])
             with torch.cuda.device(ps[0].device):
                 _lib.check(lib.selavi_sgd_step_host(params, grads, bufs, sizes, n, float(group["lr"]), float(group["momentum"]),
-                                                    float(group["weight_decay"]), 1 if first else 0, _lib.stream_ptr()),
+                                                    float(group["weight_decay"]), 0, _lib.stream_ptr()),
                            "selavi_sgd_step_host")
             # the kernel wrote the parameters behind autograd's back: bump their version counters so that
             # version-keyed caches (the packed tensor-core weights in engine.py) see the update

@@ -19,7 +19,7 @@ from . import _lib
 from .symm import SymmetricBuffer
 
 __all__ = ["optimize_L_sk_gpu", "optimize_L_sk_multi", "optimize_L_sk_sharded", "sk_solve_raw", "SKWorkspace", "SKComm",
-           "softmax_product", "get_cluster_assignments_gpu", "cluster", "match_order", "shard_range", "assemble_labels"]
+           "optimize_L_sk_gathered", "softmax_product", "softmax64", "l1_cost_matrix", "get_cluster_assignments_gpu", "cluster", "match_order", "shard_range", "assemble_labels"]
 
 
 class SKWorkspace:
@@ -182,6 +182,46 @@ def assemble_labels(L, idx_all, lab_all, head):
 _comm_cache = {}
 
 
+def _sk_comm(K, group):
+    """SKComm for (K, group), or None when the in-kernel NVSwitch exchange is unavailable (more than 8 ranks, ranks on
+    several hosts, CUDA IPC refused).  The decision is collective — SymmetricBuffer raises on every rank or on none — so
+    all ranks take the same branch."""
+    import torch.distributed as dist
+    key = (K, id(group))
+    if key not in _comm_cache:
+        comm = None
+        if dist.get_world_size(group) <= 8:
+            try:
+                comm = SKComm(K, group)
+            except _lib.SelaviError as e:
+                import warnings
+                warnings.warn(f"selavi_b200: P2P exchange for the sharded Sinkhorn-Knopp solve unavailable ({e}); gathering the "
+                              "matrix to rank 0 over NCCL like the reference (src/sk_utils.py:214-242)")
+        _comm_cache[key] = comm
+    return _comm_cache[key]
+
+
+def optimize_L_sk_gathered(args, PS_local, hc, group=None, logger=None):
+    """Fallback of the sharded solve for any world size / multi-node (the reference's own data flow, src/sk_utils.py:
+    214-242,287-327): the row shards are gathered on rank 0 over NCCL, rank 0 runs the single-GPU solver kernel and the
+    labels are broadcast.  Returns (cost, labels of ALL rows in rank-major order) on every rank."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    root = dist.get_global_rank(group, 0) if group is not None else 0
+    n_local, K = PS_local.shape
+    shards = [torch.empty_like(PS_local) for _ in range(world)] if rank == 0 else None
+    dist.gather(PS_local, shards, dst=root, group=group)
+    labels = torch.empty(n_local * world, dtype=torch.int64, device=PS_local.device)
+    cost = torch.zeros(1, dtype=torch.float64, device=PS_local.device)
+    if rank == 0:
+        c, lab = optimize_L_sk_gpu(args, torch.cat(shards), hc, logger=logger)
+        labels.copy_(lab)
+        cost[0] = c
+    dist.broadcast(labels, root, group=group)
+    dist.broadcast(cost, root, group=group)
+    return float(cost.item()), labels
+
+
 def _unwrap(model):
     return model.module if hasattr(model, "module") else model
 
@@ -247,16 +287,17 @@ def get_cluster_assignments_gpu(args, dataset, model, logger=None, writer=None, 
                     la = getattr(net, f"mlp_a{head}").forward(F_a)
                 PS = softmax_product(lv, la)
             if world > 1:
-                comm = _comm_cache.get((PS.shape[1], id(group)))
-                if comm is None:
-                    comm = SKComm(PS.shape[1], group)
-                    _comm_cache[(PS.shape[1], id(group))] = comm
-                cost, L_head = optimize_L_sk_sharded(args, PS, head, n_local * world, comm, logger=logger)
+                comm = _sk_comm(PS.shape[1], group)
                 gathered_idx = [torch.empty_like(idx_local) for _ in range(world)]
-                gathered_lab = [torch.empty_like(L_head) for _ in range(world)]
                 dist.all_gather(gathered_idx, idx_local, group=group)
-                dist.all_gather(gathered_lab, L_head, group=group)
-                assemble_labels(L, torch.cat(gathered_idx), torch.cat(gathered_lab), head)
+                if comm is not None:
+                    cost, L_head = optimize_L_sk_sharded(args, PS, head, n_local * world, comm, logger=logger)
+                    gathered_lab = [torch.empty_like(L_head) for _ in range(world)]
+                    dist.all_gather(gathered_lab, L_head, group=group)
+                    lab_all = torch.cat(gathered_lab)
+                else:
+                    cost, lab_all = optimize_L_sk_gathered(args, PS, head, group=group, logger=logger)
+                assemble_labels(L, torch.cat(gathered_idx), lab_all, head)
             else:
                 cost, L_head = optimize_L_sk_gpu(args, PS, hc=head, logger=logger)
                 assemble_labels(L, idx_local, L_head, head)
@@ -275,13 +316,32 @@ def get_cluster_assignments_gpu(args, dataset, model, logger=None, writer=None, 
     return L
 
 
+def softmax64(logits):
+    """float64 softmax of fp32 head outputs (torch.nn.functional.softmax(x, dim=1, dtype=torch.float64),
+    src/sk_utils.py:272-275) in one kernel."""
+    if not (logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == 2):
+        raise ValueError("softmax64 needs a float32 CUDA matrix")
+    logits = logits.contiguous()
+    n, K = logits.shape
+    out = torch.empty((n, K), dtype=torch.float64, device=logits.device)
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().selavi_sk_softmax64(_lib.ptr(logits), n, K, _lib.ptr(out), _lib.stream_ptr()), "selavi_sk_softmax64")
+    return out
+
+
 def l1_cost_matrix(P1, P2):
-    """C[i, j] = sum_n |P1[n, i] - P2[n, j]|  (the quantity `c(a, b)` of src/sk_utils.py:430-431 for all column pairs)."""
-    K = P1.shape[1]
+    """C[i, j] = sum_n |P1[n, i] - P2[n, j]|  (the quantity `c(a, b)` of src/sk_utils.py:430-431 for all column pairs),
+    float64, one CUDA kernel + a fixed-order split-N reduce (csrc/match.cu)."""
+    if not (P1.is_cuda and P1.dtype == torch.float64 and P2.dtype == torch.float64 and P1.shape == P2.shape and P1.dim() == 2):
+        raise ValueError("l1_cost_matrix needs two float64 CUDA matrices of equal shape [N, K]")
+    P1, P2 = P1.contiguous(), P2.contiguous()
+    n, K = P1.shape
+    lib = _lib.lib()
     C = torch.empty((K, K), dtype=torch.float64, device=P1.device)
-    P1, P2 = P1.to(torch.float64), P2.to(torch.float64)
-    for i0 in range(0, K, 16):           # chunked broadcast keeps the temporary at N*16*K elements
-        C[i0:i0 + 16] = (P1[:, i0:i0 + 16, None] - P2[:, None, :]).abs().sum(0)
+    ws = torch.empty(lib.selavi_l1_cost_workspace_bytes(n, K) // 8, dtype=torch.float64, device=P1.device)
+    with torch.cuda.device(P1.device):
+        _lib.check(lib.selavi_l1_cost_matrix(_lib.ptr(P1), _lib.ptr(P2), n, K, _lib.ptr(C), _lib.ptr(ws), _lib.stream_ptr()),
+                   "selavi_l1_cost_matrix")
     return C
 
 
@@ -296,10 +356,9 @@ def match_order(args, emb1, emb2_in, W2, steps=50000, restarts=2, logger=None, g
     import torch.distributed as dist
     distributed = dist.is_available() and dist.is_initialized()
     if logits and emb1 is not None:
-        emb1 = torch.softmax(emb1.double(), dim=1)
-        emb2_in = torch.softmax(emb2_in.double(), dim=1)
+        emb1, emb2_in = softmax64(emb1), softmax64(emb2_in)
     K = len(W2.bias.data)
-    C = l1_cost_matrix(emb1, emb2_in)
+    C = l1_cost_matrix(emb1.double(), emb2_in.double())
     if distributed and dist.get_world_size(group) > 1:
         dist.all_reduce(C, group=group)
     fin_perm = np.arange(K)
@@ -337,9 +396,57 @@ def match_order(args, emb1, emb2_in, W2, steps=50000, restarts=2, logger=None, g
     return fin
 
 
+def _log_label_metrics(args, new, old, dataset, sk_counter, logger, writer, iter_num):
+    """Host-side bookkeeping around the assignment (src/sk_utils.py:36-118): NMI of the first head against the previous
+    labels and against the dataset's ground truth, adjusted NMI, and every 10th call the per-cluster entropy / purity.
+    Pure logging (scikit-learn / scipy on the CPU, as in the reference); skipped quietly when those are not installed."""
+    import numpy as np
+    try:
+        from scipy.stats import entropy
+        from sklearn.metrics.cluster import adjusted_mutual_info_score, normalized_mutual_info_score
+    except ImportError:
+        return
+    info = logger.info if (logger is not None and args.rank == 0) else (lambda *_a, **_k: None)
+    scalar = writer.add_scalar if writer else (lambda *_a, **_k: None)
+    mine = new[:, 0].cpu().numpy()
+    nmi_prev = normalized_mutual_info_score(mine, old[:, 0].cpu().numpy(), average_method='arithmetic')
+    info(f'NMI_v: {nmi_prev}')
+    scalar('train/nmi_v/iter', nmi_prev, iter_num)
+    scalar('train/optim_count/iter', sk_counter, iter_num)
+    truth = np.array(dataset._labels)[dataset.valid_indices]
+    nmi_gt = normalized_mutual_info_score(mine, truth, average_method='arithmetic')
+    anmi_gt = adjusted_mutual_info_score(mine, truth, average_method='arithmetic')
+    info(f"NMI-tolabels: {nmi_gt}")
+    info(f"aNMI-tolabels: {anmi_gt}")
+    scalar('train/nmi-tolabels_v/iter', nmi_gt, iter_num)
+    scalar('train/a-nmi-tolabels_v/iter', anmi_gt, iter_num)
+    if sk_counter % 10 == 0:
+        ents, purs = [], []
+        for k in np.unique(mine):
+            _, counts = np.unique(truth[mine == k], return_counts=True)
+            frac = counts / counts.sum()
+            purs.append(frac.max())
+            ents.append(entropy(frac))
+        if logger is not None:
+            logger.info(f"Avg entropy: {np.mean(ents)}")
+            logger.info(f"Avg purity: {np.mean(purs)}")
+        if writer:
+            writer.add_histogram('train/entropies', np.array(ents), iter_num)
+            writer.add_histogram('train/purities', np.array(purs), iter_num)
+            writer.add_scalar('train/avg-entropy', np.mean(ents), iter_num)
+            writer.add_scalar('train/avg-purity', np.mean(purs), iter_num)
+
+
 def cluster(args, selflabels, dataset, model, sk_counter, logger, writer, group, iter_num):
-    """src/sk_utils.py:23-134 without the CPU-side NMI/purity logging (out of scope): returns the
-    new labels on every rank."""
+    """src/sk_utils.py:23-134: new pseudo-labels on every rank, the reference's NMI / purity logging (same logger lines
+    and tensorboard tags), and the closing barrier.  The SLURM requeue hook (SIGNAL_RECEIVED, :120-125) is job control
+    and stays with the reference's launcher."""
+    import torch.distributed as dist
+    old = selflabels.clone()
     with torch.no_grad():
         selflabels = get_cluster_assignments_gpu(args, dataset, model, logger, writer, group, iter_num)
+    sk_counter += 1
+    _log_label_metrics(args, selflabels, old, dataset, sk_counter, logger, writer, iter_num)
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier(group=group)
     return selflabels

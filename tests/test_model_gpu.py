@@ -93,6 +93,74 @@ def test_eval_features_match_reference(cuda_device, name):
     assert ev < 1e-3 and ea < 1e-3
 
 
+def test_benchmark_shape_streams_are_bit_reproducible(cuda_device):
+    """configs[1] shapes (batch 16, 3x32x112x112 + 1x257x200, K=309, 10 heads), where the chunked BN-statistics reduction
+    (nchunk > 1) runs on the video stream, the audio stream and the weight-gradient side streams at the same time: the
+    step must be bit-identical run to run and with the audio / weight-gradient streams switched off (the
+    per-device reduction scratch used to be shared between streams)."""
+    from selavi_b200 import engine, model as sv_model
+    from selavi_b200.utils import get_loss
+    name = "big_cfg2"
+    B, T, HW, ST, K, hc = CONFIGS[name]
+    video, spec, labels = make_inputs(name)
+    v, s, lab = (torch.from_numpy(x).to(cuda_device) for x in (video, spec, labels))
+
+    def run(audio_stream, wgrad_stream):
+        old = engine.AUDIO_STREAM, engine.WGRAD_STREAM
+        engine.AUDIO_STREAM, engine.WGRAD_STREAM = audio_stream, wgrad_stream
+        try:
+            m = build(sv_model.load_model, name).to(cuda_device).train()
+            fv, fa = m(v, s)
+            loss = 0.5 * get_loss(fv, lab, headcount=hc) + 0.5 * get_loss(fa, lab, headcount=hc)
+            loss.backward()
+            torch.cuda.synchronize()
+            return float(loss), {n: p.grad.clone() for n, p in m.named_parameters()}, {n: b.clone() for n, b in m.named_buffers()}
+        finally:
+            engine.AUDIO_STREAM, engine.WGRAD_STREAM = old
+
+    l0, g0, b0 = run(True, True)
+    for cfg in [(True, True), (False, True), (False, False)]:
+        l1, g1, b1 = run(*cfg)
+        assert l1 == l0, (cfg, l0, l1)
+        for n in g0:
+            assert torch.equal(g0[n], g1[n]), (cfg, n)
+        for n in b0:
+            assert torch.equal(b0[n], b1[n]), (cfg, n)
+
+
+def test_ce_rejects_out_of_range_labels(cuda_device):
+    """a label outside [0, K) poisons the loss and its gradient row with NaN (torch raises a device assert there)"""
+    from selavi_b200.utils import get_loss
+    x = torch.randn(4, 7, device=cuda_device, requires_grad=True)
+    t = torch.tensor([0, 6, 7, 1], device=cuda_device)
+    loss = get_loss(x, t)
+    loss.backward()
+    assert torch.isnan(loss)
+    assert torch.isnan(x.grad[2]).all() and torch.isfinite(x.grad[[0, 1, 3]]).all()
+
+
+def test_sgd_first_step_is_per_parameter(cuda_device):
+    """a parameter that receives its first gradient at a later step must not reset the other parameters' momentum"""
+    from selavi_b200.optim import SGD
+    g = torch.Generator(device=cuda_device).manual_seed(4)
+    ps = [torch.randn(n, device=cuda_device, generator=g) for n in (33, 1000)]
+    a = [torch.nn.Parameter(p.clone()) for p in ps]
+    b = [torch.nn.Parameter(p.clone()) for p in ps]
+    oa = SGD(a, lr=0.05, momentum=0.9, weight_decay=1e-4)
+    ob = torch.optim.SGD(b, lr=0.05, momentum=0.9, weight_decay=1e-4)
+    for step in range(3):
+        for i, (x, y) in enumerate(zip(a, b)):
+            if i == 1 and step == 0:
+                x.grad = y.grad = None          # second tensor: no gradient on the first step
+                continue
+            gr = torch.randn(x.shape, device=cuda_device, generator=g)
+            x.grad, y.grad = gr.clone(), gr.clone()
+        oa.step()
+        ob.step()
+    for x, y in zip(a, b):
+        torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-7)
+
+
 def test_sgd_matches_torch(cuda_device):
     from selavi_b200.optim import SGD
     g = torch.Generator(device=cuda_device).manual_seed(1)

@@ -127,3 +127,159 @@ def test_match_order_matches_oracle(cuda_device):
     assert torch.equal(lin.weight.data, w0[fin]) and torch.equal(lin.bias.data, b0[fin])
     # the search must actually have aligned the heads: emb2[:, perm] ~ emb1
     assert np.abs(sm(lv) - sm(la)[:, ref]).sum() < 0.2 * np.abs(sm(lv) - sm(la)).sum()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,K", [(7, 12), (400, 28), (5000, 309), (1531, 400)])
+def test_l1_cost_matrix_kernel(cuda_device, N, K):
+    """csrc/match.cu: C[i,j] = sum_n |P1[n,i] - P2[n,j]| and the float64 softmax feeding it, against numpy."""
+    from oracle.sk_oracle import softmax64 as sm
+    from selavi_b200.sk_utils import l1_cost_matrix, softmax64
+    rng = np.random.default_rng(N + K)
+    lv = (rng.standard_normal((N, K)) * 3).astype(np.float32)
+    la = (rng.standard_normal((N, K)) * 3).astype(np.float32)
+    Pv, Pa = softmax64(torch.from_numpy(lv).to(cuda_device)), softmax64(torch.from_numpy(la).to(cuda_device))
+    np.testing.assert_allclose(Pv.cpu().numpy(), sm(lv), rtol=1e-13, atol=0)
+    C = l1_cost_matrix(Pv, Pa).cpu().numpy()
+    ref = np.abs(sm(lv)[:, :, None] - sm(la)[:, None, :]).sum(0) if N * K * K < 5e7 else \
+        np.stack([np.abs(sm(lv)[:, i:i + 1] - sm(la)).sum(0) for i in range(K)])
+    np.testing.assert_allclose(C, ref, rtol=1e-12, atol=1e-15)
+    C2 = l1_cost_matrix(Pv, Pa).cpu().numpy()
+    assert np.array_equal(C, C2)                     # fixed-order split-N reduce: bit-reproducible
+
+
+@pytest.mark.gpu
+def test_match_order_k309_matches_oracle(cuda_device):
+    """cfg-2/3 size of the head alignment (K = 309): same permutation as the reference's search for the same np.random
+    stream, although every cost comes from the precomputed K x K matrix instead of per-step column sums."""
+    from oracle.sk_oracle import match_order_oracle, softmax64 as sm
+    from selavi_b200.sk_utils import match_order
+    rng = np.random.default_rng(9)
+    N, K = 2000, 309
+    true_perm = rng.permutation(K)
+    lv = (rng.standard_normal((N, K)) * 3).astype(np.float32)
+    la = (lv[:, true_perm] + 0.05 * rng.standard_normal((N, K))).astype(np.float32)
+    np.random.seed(5)
+    ref = match_order_oracle(sm(lv), sm(la), steps=6000)
+    lin = torch.nn.Linear(5, K).to(cuda_device)
+    w0 = lin.weight.data.clone()
+    np.random.seed(5)
+    fin = match_order(types.SimpleNamespace(rank=0), torch.from_numpy(lv).to(cuda_device), torch.from_numpy(la).to(cuda_device),
+                      lin, steps=6000, logits=True)
+    assert np.array_equal(fin.cpu().numpy(), ref)
+    assert torch.equal(lin.weight.data, w0[fin])
+
+
+def _sweep_args(**kw):
+    base = dict(world_size=1, rank=0, workers=0, ind_groups=1, headcount=1, match=False, distribution="default", dist=None,
+                diff_dist_every=False, diff_dist_per_head=True, gauss_sd=0.1, lamb=20.0, dump_path="")
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+def _head_logits(m, ds, dev, hc):
+    """eval-mode outputs of every head on the whole dataset, dataset-index order (inputs of the bookkeeping oracle)"""
+    m.eval()
+    with torch.no_grad():
+        if hc == 1:
+            lv, la = m(ds.v.to(dev), ds.a.to(dev))
+            out = [lv.cpu().numpy()], [la.cpu().numpy()]
+        else:
+            m.return_features = True
+            fv, fa = m(ds.v.to(dev), ds.a.to(dev))
+            m.return_features = False
+            out = ([getattr(m, f"mlp_v{h}").forward(fv).cpu().numpy() for h in range(hc)],
+                   [getattr(m, f"mlp_a{h}").forward(fa).cpu().numpy() for h in range(hc)])
+    m.train()
+    return out
+
+
+@pytest.mark.gpu
+def test_sweep_cfg4_match_ind_groups(cuda_device):
+    """BASELINE.json configs[3] (cfg-4) flow of `get_cluster_assignments_gpu`: K = 28, 10 heads, `match` on the first SK
+    call, ind_groups = 2 (two sweeps, heads dealt `order_heads[g::2]`), per-head Gaussian marginals, N = 3328 (AVE size).
+    Checked against the CPU bookkeeping oracle (oracle/sk_oracle.py:cluster_assignments_oracle, src/sk_utils.py:183-327)
+    fed with the same head outputs: labels of every head, the permutation applied to every audio head, model state."""
+    from oracle.sk_oracle import cluster_assignments_oracle
+    from selavi_b200 import model as sv_model
+    from selavi_b200.sk_utils import get_cluster_assignments_gpu
+    torch.manual_seed(31)
+    hc, K, N = 10, 28, 3328
+    m = sv_model.load_model(use_mlp=True, headcount=hc, num_classes=K, norm_feat=False).to(cuda_device)
+    ds = _Clips(N)
+    lv, la = _head_logits(m, ds, cuda_device, hc)
+    rng = np.random.default_rng(2)
+    kd = [(rng.standard_normal(K) * 0.1 + 1) * N / K for _ in range(hc)]
+    args = _sweep_args(ind_groups=2, headcount=hc, match=True, distribution="gauss",
+                       dist=[torch.from_numpy(k.copy()).view(K, 1).to(cuda_device) for k in kd])
+    w_before = [list(getattr(m, f"mlp_a{h}").modules())[-1].weight.data.clone() for h in range(hc)]
+    np.random.seed(7)
+    L = get_cluster_assignments_gpu(args, ds, m, logger=None, iter_num=0)
+    np.random.seed(7)
+    L_ref, perms, order = cluster_assignments_oracle(lv, la, N, 1, 2, True, kdists=kd)
+    assert sorted(perms) == list(range(hc)) and sorted(order) == list(range(hc))
+    for h in range(hc):
+        lin = list(getattr(m, f"mlp_a{h}").modules())[-1]
+        assert torch.equal(lin.weight.data, w_before[h][torch.from_numpy(perms[h]).to(cuda_device)]), h
+        assert np.array_equal(L[:, h].cpu().numpy(), L_ref[:, h]), (h, int((L[:, h].cpu().numpy() != L_ref[:, h]).sum()))
+    assert m.training and m.return_features is False
+    # a later SK call (iter_num > 0) must not re-align the heads
+    np.random.seed(8)
+    w_mid = [list(getattr(m, f"mlp_a{h}").modules())[-1].weight.data.clone() for h in range(hc)]
+    get_cluster_assignments_gpu(args, ds, m, logger=None, iter_num=5)
+    for h in range(hc):
+        assert torch.equal(list(getattr(m, f"mlp_a{h}").modules())[-1].weight.data, w_mid[h])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("match", [False, True])
+def test_sweep_single_head_branch(cuda_device, match):
+    """headcount == 1 branch (src/sk_utils.py:206-211,301-303): the model's own outputs are soft-maxed and multiplied;
+    with `match` the audio head is permuted but the assignment still uses the outputs gathered before it."""
+    from oracle.sk_oracle import cluster_assignments_oracle
+    from selavi_b200 import model as sv_model
+    from selavi_b200.sk_utils import get_cluster_assignments_gpu
+    torch.manual_seed(31)
+    K, N = 28, 203                       # N % world_size == 0 here; the remainder rule is covered by the gloo test
+    m = sv_model.load_model(use_mlp=True, headcount=1, num_classes=K, norm_feat=False).to(cuda_device)
+    ds = _Clips(N)
+    lv, la = _head_logits(m, ds, cuda_device, 1)
+    args = _sweep_args(match=match)
+    w0 = list(m.mlp_a.modules())[-1].weight.data.clone()
+    np.random.seed(3)
+    L = get_cluster_assignments_gpu(args, ds, m, logger=None, iter_num=0)
+    np.random.seed(3)
+    L_ref, perms, _ = cluster_assignments_oracle(lv, la, N, 1, 1, match)
+    assert tuple(L.shape) == (N, 1)
+    assert np.array_equal(L[:, 0].cpu().numpy(), L_ref[:, 0])
+    if match:
+        assert torch.equal(list(m.mlp_a.modules())[-1].weight.data, w0[torch.from_numpy(perms[0]).to(cuda_device)])
+    assert m.training and m.return_features is False
+
+
+@pytest.mark.gpu
+def test_sweep_against_cpu_oracle_towers(cuda_device):
+    """End to end against the CPU oracle INCLUDING the towers (oracle/model_oracle.py in eval mode -> heads -> softmax ->
+    SK): the GPU features carry ~1e-4 relative rounding differences, so rows whose two best clusters are within that
+    margin may flip; at least 97 % of the labels must agree (measured: see the printed fraction)."""
+    from oracle.model_oracle import OracleAVModel
+    from oracle.sk_oracle import cluster_assignments_oracle
+    from selavi_b200 import model as sv_model
+    from selavi_b200.sk_utils import get_cluster_assignments_gpu
+    hc, K, N = 2, 8, 160
+    torch.manual_seed(31)
+    m = sv_model.load_model(use_mlp=True, headcount=hc, num_classes=K, norm_feat=False)
+    o = OracleAVModel(hc, K)
+    o.load_state_dict(m.state_dict())
+    ds = _Clips(N)
+    o.eval()
+    with torch.no_grad():
+        ov, oa = o(ds.v, ds.a)
+    m = m.to(cuda_device)
+    np.random.seed(1)
+    L = get_cluster_assignments_gpu(_sweep_args(headcount=hc), ds, m, logger=None)
+    np.random.seed(1)
+    L_ref, _, _ = cluster_assignments_oracle([x.numpy() for x in ov], [x.numpy() for x in oa], N, 1, 1, False)
+    agree = float((L.cpu().numpy() == L_ref).mean())
+    print(f"sweep vs full CPU oracle (towers included): {agree * 100:.1f} % of {N * hc} labels agree")
+    assert agree >= 0.97

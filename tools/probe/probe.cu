@@ -4,9 +4,22 @@
 // (K-major / MN-major, swizzle modes, LBO/SBO meaning) on real hardware.
 #include <stdint.h>
 
-#include "../../include/selavi_b200.h"
-#include "common.cuh"
-#include "ptx.cuh"
+// Built into its own library (tools/probe/libselavi_probe.so, see tools/probe/__init__.py): diagnostics are not part of
+// the product C ABI.
+#include <stdio.h>
+
+#include "../../selavi_b200/csrc/ptx.cuh"
+
+static int probe_fail(int code, const char* msg) {
+    fprintf(stderr, "selavi_debug_umma_probe: %s\n", msg);
+    return code;
+}
+#define selavi_fail probe_fail
+#define SV_CUDA_CHECK(expr, what)                                              \
+    do {                                                                       \
+        cudaError_t _e = (expr);                                               \
+        if (_e != cudaSuccess) return probe_fail(-(1000 + (int)_e), what);     \
+    } while (0)
 
 namespace {
 __global__ void __launch_bounds__(160, 1)

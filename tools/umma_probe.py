@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from selavi_b200 import _lib  # noqa: E402
+from tools.probe import probe_lib  # noqa: E402
 
 
 def desc_bits(lbo, sbo, layout):
@@ -86,7 +87,7 @@ def img_mnmajor_noswz(X, nk, swap=False):
 
 
 def run(a_img, a_offs, a_bits, b_img, b_offs, b_bits, idesc_v, N, dev):
-    lib = _lib.lib()
+    lib = probe_lib()
     a = torch.from_numpy(np.ascontiguousarray(a_img)).to(dev)
     b = torch.from_numpy(np.ascontiguousarray(b_img)).to(dev)
     ao = torch.tensor(a_offs, dtype=torch.int32, device=dev)
@@ -96,7 +97,7 @@ def run(a_img, a_offs, a_bits, b_img, b_offs, b_bits, idesc_v, N, dev):
     code = lib.selavi_debug_umma_probe(_lib.ptr(a), pad(a), _lib.ptr(b), pad(b), ctypes.c_ulonglong(a_bits),
                                        ctypes.c_ulonglong(b_bits), idesc_v, len(a_offs), _lib.ptr(ao), _lib.ptr(bo), N, 0,
                                        _lib.ptr(out), _lib.stream_ptr())
-    _lib.check(code, "probe")
+    assert code == 0, f"probe failed with code {code}"
     torch.cuda.synchronize()
     return out.cpu().numpy()
 

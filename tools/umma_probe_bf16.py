@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from selavi_b200 import _lib  # noqa: E402
+from tools.probe import probe_lib  # noqa: E402
 
 
 def desc_bits(lbo, sbo, layout):
@@ -66,7 +67,7 @@ def img_mn_sw128(X, nk, swap=False, order="kg_outer"):
 
 def run(a, b, idesc_v, N, dev):
     (a_img, a_offs, a_bits), (b_img, b_offs, b_bits) = a, b
-    lib = _lib.lib()
+    lib = probe_lib()
     at = torch.from_numpy(np.ascontiguousarray(a_img).view(np.int16)).to(dev)
     bt = torch.from_numpy(np.ascontiguousarray(b_img).view(np.int16)).to(dev)
     ao = torch.tensor(a_offs, dtype=torch.int32, device=dev)
@@ -76,7 +77,7 @@ def run(a, b, idesc_v, N, dev):
     code = lib.selavi_debug_umma_probe(_lib.ptr(at), pad(at), _lib.ptr(bt), pad(bt), ctypes.c_ulonglong(a_bits),
                                        ctypes.c_ulonglong(b_bits), idesc_v, len(a_offs), _lib.ptr(ao), _lib.ptr(bo), N, 1,
                                        _lib.ptr(out), _lib.stream_ptr())
-    _lib.check(code, "probe")
+    assert code == 0, f"probe failed with code {code}"
     torch.cuda.synchronize()
     return out.cpu().numpy()
 

@@ -16,6 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from selavi_b200 import _lib  # noqa: E402
+from tools.probe import probe_lib  # noqa: E402
 
 
 def desc_bits(lbo, sbo, layout, base_off=0):
@@ -50,7 +51,7 @@ def img_rows_sw128(X, fmt):
 
 
 def run(a_img, a_offs, a_bits, b_img, b_offs, b_bits, idesc_v, N, dev):
-    lib = _lib.lib()
+    lib = probe_lib()
     at = torch.from_numpy(np.ascontiguousarray(a_img).view(np.int16)).to(dev)
     bt = torch.from_numpy(np.ascontiguousarray(b_img).view(np.int16)).to(dev)
     ao = torch.tensor(a_offs, dtype=torch.int32, device=dev)
@@ -60,7 +61,7 @@ def run(a_img, a_offs, a_bits, b_img, b_offs, b_bits, idesc_v, N, dev):
     code = lib.selavi_debug_umma_probe(_lib.ptr(at), pad(at), _lib.ptr(bt), pad(bt), ctypes.c_ulonglong(a_bits),
                                        ctypes.c_ulonglong(b_bits), idesc_v, len(a_offs), _lib.ptr(ao), _lib.ptr(bo), N, 1,
                                        _lib.ptr(out), _lib.stream_ptr())
-    _lib.check(code, "probe")
+    assert code == 0, f"probe failed with code {code}"
     torch.cuda.synchronize()
     return out.cpu().numpy()
 
