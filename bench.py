@@ -255,6 +255,28 @@ def run_ours(args):
     video_h, spec_h, labels_h = video_h.pin_memory(), spec_h.pin_memory(), labels_h.pin_memory()
     video_d, spec_d, labels_d = video_h.to(dev), spec_h.to(dev), labels_h.to(dev)
 
+    # fast mode (single-pass MMAs): error of the 512-d video features against parity mode on the FRESH weights (train-mode
+    # BatchNorm, same batch).  Features, not logits: the bench batch is 16 i.i.d. white-noise clips whose features are
+    # nearly identical, and the heads' BatchNorm1d over such a batch amplifies ANY rounding difference ~100x (for logits on
+    # a well-conditioned batch see profiles/r02_precision_modes.txt: 1.4e-2 fast vs 6.0e-5 parity at this shape).
+    fast_err = None
+    if not args.no_fast_mode:
+        try:
+            model.return_features = True
+            with torch.no_grad():
+                f3, _ = net(video_d, spec_d)
+                old_passes, engine.PASSES = engine.PASSES, 1
+                try:
+                    f1, _ = net(video_d, spec_d)
+                finally:
+                    engine.PASSES = old_passes
+                fast_err = float((f1.double() - f3.double()).norm() / f3.double().norm())
+            del f3, f1
+        except Exception as e:  # noqa: BLE001
+            fast_err = repr(e)[:200]
+        finally:
+            model.return_features = False
+
     def train_step(video, spec, labels):
         fv, fa = net(video, spec)
         loss = 0.5 * get_loss(fv, labels, hc) + 0.5 * get_loss(fa, labels, hc)
@@ -506,18 +528,12 @@ def run_ours(args):
         model.return_features = False
         model.train()
 
-    # ---- fast mode: single-pass MMAs (tf32 / fp16 / bf16 operands, SELAVI_MMA_PASSES=1) and its logit error vs parity mode
+    # ---- fast mode: single-pass MMAs (SELAVI_MMA_PASSES=1; every conv on the tf32 implicit-GEMM kernels)
     fast = None
     if not args.no_fast_mode:
         try:
-            with torch.no_grad():
-                fv3, _ = net(video_d, spec_d)
-                ref_logits = torch.stack(list(fv3)).double()
             old_passes, engine.PASSES = engine.PASSES, 1
             try:
-                with torch.no_grad():
-                    fv1, _ = net(video_d, spec_d)
-                    err = float((torch.stack(list(fv1)).double() - ref_logits).norm() / ref_logits.norm())
                 for _ in range(3):
                     train_step(video_d, spec_d, labels_d)
                 nf = max(3, min(args.steps, 10))
@@ -525,8 +541,10 @@ def run_ours(args):
             finally:
                 engine.PASSES = old_passes
             fast = {"value": B * world / (ms_fast * 1e-3), "unit": "clips/s", "ms_per_step": ms_fast, "steps": nf,
-                    "video_logit_rel_err_vs_parity_mode": err,
-                    "note": "single-pass tf32 MMAs (SELAVI_MMA_PASSES=1): outside the 1e-3 parity bar, reported for reference only"}
+                    "video_feature_rel_err_vs_parity_mode": fast_err,
+                    "note": "single-pass tf32 MMAs on the implicit-GEMM kernels only (the tap-reuse fp16x3 kernels have no single-pass "
+                            "variant, so this mode is SLOWER than parity mode; train-mode logits 1.4e-2 off, "
+                            "profiles/r02_precision_modes.txt): kept as a numerics reference point, not as a product mode"}
         except Exception as e:  # noqa: BLE001
             fast = {"error": repr(e)[:300]}
 

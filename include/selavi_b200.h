@@ -100,10 +100,12 @@ int selavi_conv_wgrad_bf16(const float* src, const void* z_hi, const void* z_lo,
                            const float* pro_scale, const float* pro_shift, int pro_relu, void* workspace, int accumulate,
                            int passes, void* stream);
 /* host-only: tiling of the bf16x3 weight gradient selavi_conv_wgrad(_bf16) will use for this geometry: 128-row tiles of the
- * flattened (tap, channel) rows, column tile width / count, row tiles per CTA (they share every dz stage), split-K slices, and
- * whether the operands are exchanged (dz as the tap-shifted row operand; stride-1 "same" convolutions only). */
+ * flattened (tap, channel) rows, column tile width / count, row tiles per CTA (they share every dz stage), the largest number
+ * of split-K slices a group of row tiles gets (slices are dealt in proportion to a group's row tiles; one wave of CTAs in
+ * total), whether the operands are exchanged (dz as the tap-shifted row operand; stride-1 "same" convolutions only), and
+ * the number of CTAs launched. */
 int selavi_conv_wgrad_plan(const int* geom, int ci_real, int* mtiles, int* bnt, int* ntiles, int* tiles_per_cta, int* slices,
-                           int* exchanged);
+                           int* exchanged, int* ctas);
 size_t selavi_dgrad_wpack_bytes(const int* geom);
 int selavi_dgrad_pack_weights(const float* W, const int* geom, int co, void* wpack, void* stream);
 int selavi_conv_dgrad_bf16(const void* z_hi, const void* z_lo, float* dx, const void* wpack, const int* geom,

@@ -90,7 +90,7 @@ SIGNATURES = {
     "selavi_sgd_step_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_int, c_void_p]),
     "selavi_mel_logfbank": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p, c_int, c_int, c_double, c_int,
                                     c_void_p, c_void_p]),
-    "selavi_conv_wgrad_plan": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "selavi_conv_wgrad_plan": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "selavi_clip_augment": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "selavi_symm_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
     "selavi_symm_open": (c_int, [c_void_p, c_void_p]),

@@ -27,6 +27,35 @@ constexpr int WG_THREADS = (WG_LOADER_WARPS + 1) * 32;
 constexpr int WG_PIX = 32;                     // pixels per stage (4 MMA K steps)
 constexpr int WG_A_BYTES = 128 * 128;          // 128 GEMM rows x 128 B (32 pixels), K-major SWIZZLE_128B
 
+// Split-K schedule: ONE wave of CTAs (148 / (groups x column tiles) slices per group) whenever the layer has that much
+// parallelism along the pixels, and the SAME slices for every group of row tiles: the groups then walk the same pixels at
+// the same time and the dz stages they all need are shared through L2.  Measured on B200 (tools/wgrad_sweep.py,
+// profiles/r02_wgrad_sweep.txt): against round 1's three waves this is 4-15 % faster on every layer (a third of the
+// partial-tile traffic, a third of the pipeline fills); dealing slices in proportion to a group's row tiles (equal MMA
+// work per CTA, but the groups drift apart) is SLOWER than equal slices by up to 25 %.
+constexpr int WG_MAX_GROUPS = 96;
+struct WgSplit {
+    int ngroups;
+    int ctas_per_ntile;              // sum of slices[g]
+    int max_slices;
+    short slices[WG_MAX_GROUPS];     // split-K slices of group g
+    int kps[WG_MAX_GROUPS];          // pixel stages per slice of group g
+    short cta0[WG_MAX_GROUPS + 1];   // first CTA (within a column tile) of group g
+};
+
+__device__ __forceinline__ void wg_locate(const WgSplit& sp, int cid, int total_kstages, int& group, int& ntile, int& slice,
+                                          int& ks_begin, int& ks_end) {
+    ntile = cid / sp.ctas_per_ntile;
+    const int r = cid - ntile * sp.ctas_per_ntile;
+    int g = 0;
+    while (g + 1 < sp.ngroups && r >= sp.cta0[g + 1]) ++g;
+    group = g;
+    slice = r - sp.cta0[g];
+    ks_begin = slice * sp.kps[g];
+    ks_end = ks_begin + sp.kps[g];
+    if (ks_end > total_kstages) ks_end = total_kstages;
+}
+
 struct WgradParams {
     const float* src;   // forward input (raw), gathered
     const float* dz;    // gradient wrt the conv output [M, cd]
@@ -38,9 +67,10 @@ struct WgradParams {
     int kt, kh, kw, st, sh, sw, pt, ph, pw;
     int M;
     int mtiles, bnt, ntiles, natom;   // natom = ceil(bnt/32)
-    int stages, total_kstages, kstages_per_slice;
+    int stages, total_kstages;
     int pro_relu, passes;
     uint32_t tmem_cols;
+    WgSplit split;
 };
 
 __device__ __forceinline__ uint32_t wg_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
@@ -85,12 +115,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const WgradParams 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int mt = blockIdx.x % p.mtiles;
-    const int ntile = blockIdx.x / p.mtiles;
-    const int slice = blockIdx.y;
-    const int ks_begin = slice * p.kstages_per_slice;
-    int ks_end = ks_begin + p.kstages_per_slice;
-    if (ks_end > p.total_kstages) ks_end = p.total_kstages;
+    int mt, ntile, slice, ks_begin, ks_end;
+    wg_locate(p.split, (int)blockIdx.x, p.total_kstages, mt, ntile, slice, ks_begin, ks_end);   // groups of one row tile
     const int nks = ks_end - ks_begin;   // >= 1 by construction
 
     if (tid == 0) {
@@ -351,9 +377,10 @@ struct WgradBf16Params {
     int M;
     int mtiles, bnt, ntiles;
     int G, groups;   // G consecutive 128-row tiles per CTA share every dz stage (one accumulator each)
-    int stages, total_kstages, kstages_per_slice;
+    int stages, total_kstages;
     int passes;
     uint32_t tmem_cols;
+    WgSplit split;
 };
 
 constexpr int WB_MAX_G = 3;
@@ -385,13 +412,10 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int mt0 = (blockIdx.x % p.groups) * p.G;
+    int group, ntile, slice, ks_begin, ks_end;
+    wg_locate(p.split, (int)blockIdx.x, p.total_kstages, group, ntile, slice, ks_begin, ks_end);
+    const int mt0 = group * p.G;
     const int nmt = p.mtiles - mt0 < p.G ? p.mtiles - mt0 : p.G;   // 128-row tiles of this CTA
-    const int ntile = blockIdx.x / p.groups;
-    const int slice = blockIdx.y;
-    const int ks_begin = slice * p.kstages_per_slice;
-    int ks_end = ks_begin + p.kstages_per_slice;
-    if (ks_end > p.total_kstages) ks_end = p.total_kstages;
     const int nks = ks_end - ks_begin;
 
     if (tid == 0) {
@@ -603,7 +627,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf
 
 // dW[co][ci][tap] (+)= sum_s partial[s][tap*cs + ci][co]
 // swapped (operands exchanged, see wgrad_run): partial[s][(taps-1-tap)*rs + co][ci], rs = channel stride of dz
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int slices, int mg_pad, int ntot, int co, int ci,
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, const WgSplit sp, int G, int mg_pad, int ntot, int co, int ci,
                                     int taps, int rs, int swapped, float* __restrict__ dW, int accumulate) {
     const size_t total = (size_t)co * ci * taps;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -630,6 +654,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int slice
         // with up to ~450 split-K slices a single dependent chain made this kernel latency bound
         const float* src = partial + row * ntot + col;
         const size_t kstride = (size_t)mg_pad * ntot;
+        const int slices = sp.slices[(int)(row >> 7) / G];   // the row tile's group decides how many slices exist
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         int k = 0;
         for (; k + 4 <= slices; k += 4) {
@@ -654,8 +679,9 @@ void wg_tiles(int n_out, int* bnt, int* ntiles) {
 }
 
 struct WgPlan {
-    int mtiles, bnt, ntiles, natom, total_kstages, slices, kstages_per_slice;
+    int mtiles, bnt, ntiles, natom, total_kstages;
     int G, groups;   // bf16 kernel: G consecutive 128-row tiles per CTA (tf32 kernel: always 1 tile per CTA)
+    WgSplit split;
 };
 
 WgPlan wg_plan(int co, int taps, int cs, long long M, bool bf16) {
@@ -680,14 +706,38 @@ WgPlan wg_plan(int co, int taps, int cs, long long M, bool bf16) {
     }
     pl.G = G;
     pl.groups = (pl.mtiles + G - 1) / G;
-    const int tiles = pl.groups * pl.ntiles;
-    int slices = (148 * 3) / tiles;  // at most 3 full waves of CTAs (no tail wave)
-    if (slices < 1) slices = 1;
-    if (slices > pl.total_kstages) slices = pl.total_kstages;
-    if (slices > 256) slices = 256;
-    if (slices < 1) slices = 1;
-    pl.kstages_per_slice = (pl.total_kstages + slices - 1) / slices;
-    pl.slices = (pl.total_kstages + pl.kstages_per_slice - 1) / pl.kstages_per_slice;
+    // split-K: one wave of CTAs, equal slices per group (see WgSplit); a layer with more (group, column tile) pairs than
+    // SMs runs one slice each
+    WgSplit& sp = pl.split;
+    sp.ngroups = pl.groups;
+    sp.ctas_per_ntile = sp.max_slices = 0;
+    if (pl.groups > WG_MAX_GROUPS) return pl;   // rejected by wgrad_run
+    // experiment knobs (tools/wgrad_sweep.py): SELAVI_WGRAD_WAVES = waves of CTAs (default 1), SELAVI_WGRAD_ALIGNED = 1 gives
+    // every group the same slices (the groups then walk the same pixels at the same time and share dz through L2)
+    static const int waves = getenv("SELAVI_WGRAD_WAVES") ? atoi(getenv("SELAVI_WGRAD_WAVES")) : 1;
+    static const int aligned = getenv("SELAVI_WGRAD_ALIGNED") ? atoi(getenv("SELAVI_WGRAD_ALIGNED")) : 1;
+    const int budget = (148 * (waves > 0 ? waves : 1)) / pl.ntiles > 0 ? (148 * (waves > 0 ? waves : 1)) / pl.ntiles : 1;
+    int used = 0, max_s = 1;
+    sp.cta0[0] = 0;
+    for (int g = 0; g < pl.groups; ++g) {
+        const int nmt = pl.mtiles - g * G < G ? pl.mtiles - g * G : G;
+        // largest-remainder style: what is left of the budget, spread over the row tiles that are left
+        const int tiles_left = pl.mtiles - g * G;
+        int sl = (int)(((long long)(budget - used) * nmt + tiles_left / 2) / tiles_left);
+        if (aligned) sl = budget / pl.groups;
+        if (sl < 1) sl = 1;
+        if (sl > pl.total_kstages) sl = pl.total_kstages;
+        if (sl > 1024) sl = 1024;
+        const int kps = (pl.total_kstages + sl - 1) / sl;
+        sl = (pl.total_kstages + kps - 1) / kps;     // no empty slice
+        sp.slices[g] = (short)sl;
+        sp.kps[g] = kps;
+        used += sl;
+        sp.cta0[g + 1] = (short)used;
+        if (sl > max_s) max_s = sl;
+    }
+    sp.ctas_per_ntile = used;
+    sp.max_slices = max_s;
     return pl;
 }
 
@@ -733,11 +783,11 @@ extern "C" size_t selavi_wgrad_workspace_bytes(const int* geom) {
     const long long Min = (long long)geom[1] * geom[2] * geom[3] * geom[4];
     const int taps = geom[10] * geom[11] * geom[12];
     const WgPlan pl = wg_plan(geom[19], taps, geom[5], M, true), pl32 = wg_plan(geom[19], taps, geom[5], M, false);
-    const int slices = pl.slices > pl32.slices ? pl.slices : pl32.slices;
+    const int slices = pl.split.max_slices > pl32.split.max_slices ? pl.split.max_slices : pl32.split.max_slices;
     size_t partial = (size_t)slices * pl.mtiles * 128 * pl.ntiles * pl.bnt * sizeof(float);
     {   // operands exchanged (wgrad_run picks it for some stride-1 convs): rows = taps * cd, columns = input channels
         const WgPlan ps = wg_plan(geom[5], taps, geom[9], M, true);
-        const size_t alt = (size_t)ps.slices * ps.mtiles * 128 * ps.ntiles * ps.bnt * sizeof(float);
+        const size_t alt = (size_t)ps.split.max_slices * ps.mtiles * 128 * ps.ntiles * ps.bnt * sizeof(float);
         if (alt > partial) partial = alt;
     }
     return align256(partial) + 2 * align256((size_t)Min * geom[5] * 2) + 2 * align256((size_t)M * geom[9] * 2) + 256;
@@ -779,7 +829,9 @@ int wgrad_run(const float* src, const float* dz, const void* z_hi_in, const void
     bool swapped = false;
     const WgPlan pl = wg_choose(geom, ci_real, bf16, &swapped);
     p.mtiles = pl.mtiles; p.bnt = pl.bnt; p.ntiles = pl.ntiles; p.natom = pl.natom;
-    p.total_kstages = pl.total_kstages; p.kstages_per_slice = pl.kstages_per_slice;
+    p.total_kstages = pl.total_kstages;
+    p.split = pl.split;
+    if (pl.groups > WG_MAX_GROUPS) return selavi_fail(-1, "conv_wgrad: too many row-tile groups");
     p.pro_relu = pro_relu;
     if (!bf16 && !dz) return selavi_fail(-1, "conv_wgrad: the tf32 path needs the fp32 gradient");
     p.passes = bf16 ? passes : passes - 10;
@@ -793,10 +845,10 @@ int wgrad_run(const float* src, const float* dz, const void* z_hi_in, const void
     if (stages < 2) return selavi_fail(-1, "conv_wgrad: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + tail_bytes + 1024;
-    dim3 grid(pl.groups * pl.ntiles, pl.slices);
+    dim3 grid(pl.split.ctas_per_ntile * pl.ntiles);
     if (bf16) {
         // operand preparation: normalise + split the conv input (and dz unless it arrives pre-split): one HBM pass each
-        const size_t partial_bytes = align256((size_t)pl.slices * pl.mtiles * 128 * pl.ntiles * pl.bnt * sizeof(float));
+        const size_t partial_bytes = align256((size_t)pl.split.max_slices * pl.mtiles * 128 * pl.ntiles * pl.bnt * sizeof(float));
         unsigned char* w = reinterpret_cast<unsigned char*>(workspace) + partial_bytes;
         const size_t a_bytes = align256((size_t)Min * p.cs * 2), z_bytes = align256((size_t)M * p.cd * 2);
         WgradBf16Params q;
@@ -827,7 +879,7 @@ int wgrad_run(const float* src, const float* dz, const void* z_hi_in, const void
         q.kt = p.kt; q.kh = p.kh; q.kw = p.kw; q.st = p.st; q.sh = p.sh; q.sw = p.sw; q.pt = p.pt; q.ph = p.ph; q.pw = p.pw;
         q.M = p.M; q.mtiles = p.mtiles; q.bnt = p.bnt; q.ntiles = p.ntiles;
         q.G = pl.G; q.groups = pl.groups;
-        q.stages = p.stages; q.total_kstages = p.total_kstages; q.kstages_per_slice = p.kstages_per_slice;
+        q.stages = p.stages; q.total_kstages = p.total_kstages; q.split = pl.split;
         q.passes = p.passes; q.tmem_cols = p.tmem_cols;
         SV_CUDA_CHECK(cudaFuncSetAttribute(wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                       "conv_wgrad: cudaFuncSetAttribute");
@@ -841,7 +893,7 @@ int wgrad_run(const float* src, const float* dz, const void* z_hi_in, const void
     const size_t total = (size_t)co * ci_real * taps;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, pl.slices, pl.mtiles * 128, pl.ntiles * pl.bnt, co, ci_real, taps,
+    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(p.partial, pl.split, pl.G, pl.mtiles * 128, pl.ntiles * pl.bnt, co, ci_real, taps,
                                                     swapped ? p.cd : p.cs, swapped ? 1 : 0, dW, accumulate);
     SV_CUDA_CHECK(cudaGetLastError(), "conv_wgrad: reduce launch");
     return 0;
@@ -850,9 +902,10 @@ int wgrad_run(const float* src, const float* dz, const void* z_hi_in, const void
 }  // namespace
 
 // host-only query: tiling of the bf16x3 weight gradient for this geometry (row tiles, column tile width, column tiles,
-// row tiles per CTA, split-K slices, and whether the operands are exchanged)
+// row tiles per CTA, the largest number of split-K slices any row-tile group gets, whether the operands are exchanged, and
+// the number of CTAs launched)
 extern "C" int selavi_conv_wgrad_plan(const int* geom, int ci_real, int* mtiles, int* bnt, int* ntiles, int* tiles_per_cta,
-                                      int* slices, int* exchanged) {
+                                      int* slices, int* exchanged, int* ctas) {
     if (!geom || ci_real <= 0) return selavi_fail(-1, "conv_wgrad_plan: bad arguments");
     bool sw = false;
     const WgPlan pl = wg_choose(geom, ci_real, true, &sw);
@@ -860,7 +913,8 @@ extern "C" int selavi_conv_wgrad_plan(const int* geom, int ci_real, int* mtiles,
     if (bnt) *bnt = pl.bnt;
     if (ntiles) *ntiles = pl.ntiles;
     if (tiles_per_cta) *tiles_per_cta = pl.G;
-    if (slices) *slices = pl.slices;
+    if (slices) *slices = pl.split.max_slices;
+    if (ctas) *ctas = pl.split.ctas_per_ntile * pl.ntiles;
     if (exchanged) *exchanged = sw ? 1 : 0;
     return 0;
 }

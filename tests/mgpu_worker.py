@@ -148,6 +148,11 @@ def main():
     hc4, K4, N4 = 4, 28, 203
     ds = Clips(N4)
     m1 = build_model(lambda: sv_model.load_model(use_mlp=True, headcount=hc4, num_classes=K4, norm_feat=False)).to(dev)
+    m1.train()
+    with torch.no_grad():      # BN warm-up (utils.py:389-418): without it ~40 % of match_order's swap deltas are exact ties
+        for it in range(25):   # (see tests/test_sweep.py:_warm_bn); same data on every rank => identical models
+            lo = (it * 32) % 160
+            m1(ds.v[lo:lo + 40].to(dev), ds.a[lo:lo + 40].to(dev))
     m1.eval()
     with torch.no_grad():
         m1.return_features = True

@@ -58,12 +58,14 @@ def test_wgrad_plan_host_logic(built_lib):
     from selavi_b200 import ops
 
     def plan(nb, ci, co, thw, k, s, p):
-        v = [ctypes.c_int() for _ in range(6)]
+        v = [ctypes.c_int() for _ in range(7)]
         assert built_lib.selavi_conv_wgrad_plan(ops.ConvGeom(nb, ci, co, thw, k, s, p).arr(0), ci, *[ctypes.byref(x) for x in v]) == 0
-        return dict(zip(("mtiles", "bnt", "ntiles", "G", "slices", "exchanged"), (x.value for x in v)))
+        return dict(zip(("mtiles", "bnt", "ntiles", "G", "slices", "exchanged", "ctas"), (x.value for x in v)))
 
     l1s = plan(16, 64, 144, (32, 56, 56), (1, 3, 3), (1, 1, 1), (0, 1, 1))
     assert (l1s["mtiles"], l1s["bnt"], l1s["ntiles"], l1s["G"], l1s["exchanged"]) == (5, 144, 1, 3, 0)
+    # split-K: one wave of 148 CTAs, 74 slices for each of the two groups of row tiles (same pixels at the same time)
+    assert (l1s["slices"], l1s["ctas"]) == (74, 148)
     l1t = plan(16, 144, 64, (32, 56, 56), (3, 1, 1), (1, 1, 1), (1, 0, 0))      # 4 row tiles x N=64 -> 2 row tiles x N=144
     assert (l1t["mtiles"], l1t["bnt"], l1t["G"], l1t["exchanged"]) == (2, 144, 2, 1)
     strided = plan(16, 64, 230, (32, 56, 56), (1, 3, 3), (1, 2, 2), (0, 1, 1))  # strided: never exchanged
@@ -76,7 +78,7 @@ def test_wgrad_plan_host_logic(built_lib):
         assert 1 <= pl["G"] <= 3 and pl["G"] * pl["bnt"] <= 512, name
         assert pl["bnt"] % 16 == 0 and pl["bnt"] <= 256 and pl["slices"] >= 1, name
         groups = -(-pl["mtiles"] // pl["G"])
-        assert groups * pl["ntiles"] * pl["slices"] <= 148 * 3 + groups * pl["ntiles"], name   # at most ~3 waves of CTAs
+        assert groups * pl["ntiles"] <= pl["ctas"] <= max(148, groups * pl["ntiles"]) + groups, name   # one wave of CTAs
 
 
 def test_halo_plan_host_logic(built_lib):

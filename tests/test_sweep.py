@@ -177,6 +177,20 @@ def _sweep_args(**kw):
     return types.SimpleNamespace(**base)
 
 
+def _warm_bn(m, ds, dev, passes=25):
+    """Train-mode no-grad forwards (the reference's `warmup_batchnorm`, utils.py:389-418, run by main.py before the first SK
+    call): with the constructor's running statistics (mean 0, var 1) the eval-mode features of an untrained tower are
+    nearly collinear across clips and the head outputs differ mostly by per-column offsets — about 40 % of the swap
+    deltas of `match_order` are then EXACT ties in exact arithmetic and their sign is rounding noise, in the reference
+    as much as here.  Warmed up, the smallest |delta| seen is 1e-5 of its scale."""
+    m.train()
+    n = len(ds)
+    with torch.no_grad():
+        for it in range(passes):
+            lo = (it * 32) % max(1, n - 40)
+            m(ds.v[lo:lo + 40].to(dev), ds.a[lo:lo + 40].to(dev))
+
+
 def _head_logits(m, ds, dev, hc):
     """eval-mode outputs of every head on the whole dataset, dataset-index order (inputs of the bookkeeping oracle)"""
     m.eval()
@@ -207,6 +221,7 @@ def test_sweep_cfg4_match_ind_groups(cuda_device):
     hc, K, N = 10, 28, 3328
     m = sv_model.load_model(use_mlp=True, headcount=hc, num_classes=K, norm_feat=False).to(cuda_device)
     ds = _Clips(N)
+    _warm_bn(m, ds, cuda_device)
     lv, la = _head_logits(m, ds, cuda_device, hc)
     rng = np.random.default_rng(2)
     kd = [(rng.standard_normal(K) * 0.1 + 1) * N / K for _ in range(hc)]
@@ -243,6 +258,7 @@ def test_sweep_single_head_branch(cuda_device, match):
     K, N = 28, 203                       # N % world_size == 0 here; the remainder rule is covered by the gloo test
     m = sv_model.load_model(use_mlp=True, headcount=1, num_classes=K, norm_feat=False).to(cuda_device)
     ds = _Clips(N)
+    _warm_bn(m, ds, cuda_device)
     lv, la = _head_logits(m, ds, cuda_device, 1)
     args = _sweep_args(match=match)
     w0 = list(m.mlp_a.modules())[-1].weight.data.clone()
