@@ -74,10 +74,13 @@ int selavi_sk_solve(double* PS, long long n_local, long long n_global, int K, do
  * pro_scale/pro_shift [cs] (nullable): fused prologue x -> x*scale+shift (+ReLU if pro_relu) on every
  *   gathered element = the train-mode BatchNorm(+ReLU) of the previous layer; zero padding stays zero.
  * stats_partial (nullable, forward): [ceil(M/128)][2][ntiles*bnt] per-tile column sum / sum of squares of dst.
- * passes: 3 = tf32x3 split (fp32-class accuracy), 1 = single tf32 pass.
+ * passes: 3 = tf32x3 split (fp32-class accuracy), 1 = single tf32 pass, 6 = fp16x3 (mode 0 only: operands split into
+ *   fp16 hi/lo with exact power-of-two scaling, 22 significant bits like tf32x3 at twice the MMA rate and half the
+ *   shared-memory bytes; wpack from selavi_conv_pack_weights mode 2, sized by selavi_conv_wpack_bytes_f16).
  */
 int selavi_conv_tiles(int n_out, int* bnt, int* ntiles);
 size_t selavi_conv_wpack_bytes(int n_out, int k_total);
+size_t selavi_conv_wpack_bytes_f16(int n_out, int k_total);
 int selavi_conv_pack_weights(const float* W, int mode, int co, int ci, int taps, int cs, void* wpack, void* stream);
 int selavi_conv_gemm(const float* src, float* dst, const void* wpack, const int* geom, const float* pro_scale,
                      const float* pro_shift, int pro_relu, float* stats_partial, int accumulate, int passes,

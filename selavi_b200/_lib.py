@@ -33,6 +33,7 @@ SIGNATURES = {
                                 c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "selavi_conv_tiles": (c_int, [c_int, c_void_p, c_void_p]),
     "selavi_conv_wpack_bytes": (c_size_t, [c_int, c_int]),
+    "selavi_conv_wpack_bytes_f16": (c_size_t, [c_int, c_int]),
     "selavi_conv_pack_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "selavi_conv_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                  c_int, c_void_p]),

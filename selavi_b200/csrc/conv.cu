@@ -19,6 +19,12 @@
 //     `passes`=1 is plain tf32.
 //   * Epilogue: TMEM -> registers -> global (float4), plus per-tile per-channel sum / sum-of-squares partials
 //     for the following BatchNorm (deterministic two-stage reduction, no atomics).
+//
+// F16 variant (passes = 6, forward of the strided / 7x7 / 1x1 convolutions): the same kernel with fp16 hi/lo operands
+// (hi = fp16(16 x), lo = fp16(16 x - hi); weights scaled by 2^8, epilogue by 2^-12: all exact, 22 significant bits like
+// tf32x3 and like the tap-reuse kernel conv_halo.cu) on tcgen05.mma.kind::f16: a 128-byte row holds 64 K elements
+// instead of 32, i.e. half the pipeline stages, half the shared-memory bytes and half the MMA instructions.
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "../../include/selavi_b200.h"
@@ -28,7 +34,10 @@
 namespace {
 
 constexpr int BM = 128;            // pixels per tile (UMMA M)
-constexpr int BK = 32;             // fp32 elements per K stage (one 128B swizzle row)
+constexpr int BK = 32;             // fp32 elements per K stage (one 128B swizzle row); the fp16 variant holds 64
+constexpr float F16_ASCALE = 16.f;
+constexpr float F16_WSCALE = 256.f;
+constexpr float F16_OSCALE = 1.f / (16.f * 256.f);
 constexpr int EPI_WARPS = 4;       // warps 0..3  : epilogue (TMEM lane quadrant = warp id)
 constexpr int LOADER_WARPS = 8;    // warps 4..19 : A-operand gather (4 per scheduler: the gather streams are latency-bound)
 constexpr int ROWS_PER = 1024 / (LOADER_WARPS * 32);   // tile rows per loader thread
@@ -69,15 +78,22 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// One gathered K stage of a loader thread: 4 rows x one 16-byte chunk, plus the prologue affine of that chunk.
+// One gathered K stage of a loader thread: 4 rows x one 16-byte shared-memory chunk (4 fp32 channels, or 8 channels of the
+// fp16 variant = NV float4 loads per row), plus the prologue affine of those channels.
+template <int NV>
 struct AStage {
-    float4 v[ROWS_PER];
-    float4 sc, sf;
+    float4 v[ROWS_PER][NV];
+    int ch;           // first channel of the chunk (the prologue affine is fetched at commit time: L1-resident, saves registers)
     uint32_t okmask;  // bit j: row j valid for this tap (prologue applies, otherwise exact zero)
 };
 
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
 // Persistent kernel: CTA b processes tiles b, b+gridDim.x, ... (tile = m_tile * ntiles + n_tile).
+template <bool F16>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvParams p) {
+    constexpr int NV = F16 ? 2 : 1;      // float4 loads per (row, chunk)
+    constexpr int CW = 4 * NV;           // channels per 16-byte shared-memory chunk
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve: [stages x (A_hi | A_lo | B_hi | B_lo)] [barriers] [tap tables] [stat scratch]
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -135,7 +151,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
         const int ltid = tid - EPI_WARPS * 32;
         const int c = ltid & 7;    // 16-byte chunk within the 128B K row
         const int r0 = ltid >> 3;  // rows r0 + ROW_STEP*j
-        const int C4 = p.cs >> 2;
+        const int C4 = p.cs / CW;      // chunk units per pixel (cs is a multiple of 8)
         const uint32_t sw_off = (uint32_t)((c ^ (r0 & 7)) << 4);
         const bool pro = p.pro_scale != nullptr;
         int stage = 0;
@@ -200,12 +216,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
                 ++tap;
             }
             // issue the gathers of one K stage into registers (no dependence on the smem ring)
-            auto gather = [&](AStage& a) {
+            auto gather = [&](AStage<NV>& a) {
                 a.okmask = 0;
-                a.sc = make_float4(1.f, 1.f, 1.f, 1.f);
-                a.sf = make_float4(0.f, 0.f, 0.f, 0.f);
+                a.ch = 0;
 #pragma unroll
-                for (int j = 0; j < ROWS_PER; ++j) a.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < ROWS_PER; ++j)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) a.v[j][v] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (tap < taps) {
                     const int pk = tap_dt[tap];
                     const int off = tap_off[tap];
@@ -214,14 +231,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
                     for (int j = 0; j < ROWS_PER; ++j) {
                         const uint32_t m_ = vm[j];
                         if ((m_ >> 31) & (m_ >> s_t) & (m_ >> s_h) & (m_ >> s_w) & 1u) {
-                            a.v[j] = __ldg(reinterpret_cast<const float4*>(p.src + (size_t)(pb[j] + off) * p.cs + c4 * 4));
+                            const float4* g = reinterpret_cast<const float4*>(p.src + (size_t)(pb[j] + off) * p.cs + c4 * CW);
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) a.v[j][v] = __ldg(g + v);
                             a.okmask |= 1u << j;
                         }
                     }
-                    if (pro) {
-                        a.sc = __ldg(reinterpret_cast<const float4*>(p.pro_scale + c4 * 4));
-                        a.sf = __ldg(reinterpret_cast<const float4*>(p.pro_shift + c4 * 4));
-                    }
+                    a.ch = c4 * CW;
                 }
                 c4 += 8;  // advance the K position by 8 chunks
                 while (c4 >= C4 && tap < taps) {
@@ -229,33 +245,57 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
                     ++tap;
                 }
             };
-            // prologue + tf32 split + swizzled store of one gathered stage, then signal the MMA warp
-            auto commit = [&](const AStage& a) {
+            // prologue + hi/lo split + swizzled store of one gathered stage, then signal the MMA warp
+            auto commit = [&](const AStage<NV>& a) {
                 sv::mbar_wait(&empty_bar[stage], phase ^ 1);
                 const uint32_t a_hi = sv::smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint32_t a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
                 for (int j = 0; j < ROWS_PER; ++j) {
-                    float4 x = a.v[j];
-                    if (pro && ((a.okmask >> j) & 1u)) {
-                        x.x = fmaf(x.x, a.sc.x, a.sf.x);
-                        x.y = fmaf(x.y, a.sc.y, a.sf.y);
-                        x.z = fmaf(x.z, a.sc.z, a.sf.z);
-                        x.w = fmaf(x.w, a.sc.w, a.sf.w);
-                        if (p.pro_relu) {
-                            x.x = fmaxf(x.x, 0.f);
-                            x.y = fmaxf(x.y, 0.f);
-                            x.z = fmaxf(x.z, 0.f);
-                            x.w = fmaxf(x.w, 0.f);
+                    float x[CW];
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        float4 t = a.v[j][v];
+                        if (pro && ((a.okmask >> j) & 1u)) {
+                            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.pro_scale + a.ch) + v);
+                            const float4 sf = __ldg(reinterpret_cast<const float4*>(p.pro_shift + a.ch) + v);
+                            t.x = fmaf(t.x, sc.x, sf.x);
+                            t.y = fmaf(t.y, sc.y, sf.y);
+                            t.z = fmaf(t.z, sc.z, sf.z);
+                            t.w = fmaf(t.w, sc.w, sf.w);
+                            if (p.pro_relu) {
+                                t.x = fmaxf(t.x, 0.f);
+                                t.y = fmaxf(t.y, 0.f);
+                                t.z = fmaxf(t.z, 0.f);
+                                t.w = fmaxf(t.w, 0.f);
+                            }
                         }
+                        x[4 * v] = t.x;
+                        x[4 * v + 1] = t.y;
+                        x[4 * v + 2] = t.z;
+                        x[4 * v + 3] = t.w;
                     }
                     const uint32_t row_off = (uint32_t)((r0 + ROW_STEP * j) * 128) + sw_off;
-                    const uint32_t h0 = tf32_hi(x.x), h1 = tf32_hi(x.y), h2 = tf32_hi(x.z), h3 = tf32_hi(x.w);
-                    st_shared_v4(a_hi + row_off, h0, h1, h2, h3);
-                    if (p.passes == 3) {
-                        st_shared_v4(a_lo + row_off, __float_as_uint(x.x - __uint_as_float(h0)),
-                                     __float_as_uint(x.y - __uint_as_float(h1)), __float_as_uint(x.z - __uint_as_float(h2)),
-                                     __float_as_uint(x.w - __uint_as_float(h3)));
+                    if constexpr (F16) {
+                        uint32_t hb[4], lb[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float x0 = x[2 * e] * F16_ASCALE, x1 = x[2 * e + 1] * F16_ASCALE;   // exact (power of two)
+                            const __half2 h = __floats2half2_rn(x0, x1);
+                            const float2 hf = __half22float2(h);
+                            hb[e] = h2_bits(h);
+                            lb[e] = h2_bits(__floats2half2_rn(x0 - hf.x, x1 - hf.y));
+                        }
+                        st_shared_v4(a_hi + row_off, hb[0], hb[1], hb[2], hb[3]);
+                        st_shared_v4(a_lo + row_off, lb[0], lb[1], lb[2], lb[3]);
+                    } else {
+                        const uint32_t h0 = tf32_hi(x[0]), h1 = tf32_hi(x[1]), h2 = tf32_hi(x[2]), h3 = tf32_hi(x[3]);
+                        st_shared_v4(a_hi + row_off, h0, h1, h2, h3);
+                        if (p.passes == 3) {
+                            st_shared_v4(a_lo + row_off, __float_as_uint(x[0] - __uint_as_float(h0)),
+                                         __float_as_uint(x[1] - __uint_as_float(h1)), __float_as_uint(x[2] - __uint_as_float(h2)),
+                                         __float_as_uint(x[3] - __uint_as_float(h3)));
+                        }
                     }
                 }
                 sv::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -267,7 +307,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
                 }
             };
             // software pipeline: the gathers of stage ks+1 are in flight while stage ks is converted and stored
-            AStage sa, sb;
+            AStage<NV> sa, sb;
             gather(sa);
             for (int ks = 0; ks < p.kstages; ks += 2) {
                 if (ks + 1 < p.kstages) gather(sb);
@@ -299,7 +339,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
             sv::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * (p.tmem_cols >> 1);
             // coalesced drain through the per-warp staging tile (+ the BN column sums), see sv::epi_drain_group
-            sv::epi_drain_tile(taddr, p.bnt, 1.f, row_ok, stg, row_pix, p.dst, p.cd, n_base, p.accumulate, true,
+            sv::epi_drain_tile(taddr, p.bnt, F16 ? F16_OSCALE : 1.f, row_ok, stg, row_pix, p.dst, p.cd, n_base, p.accumulate, true,
                                p.stats != nullptr ? my_stat : nullptr, lane);
             // accumulator drained: hand the TMEM buffer back to the MMA warp
             sv::tc_fence_before();
@@ -322,7 +362,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
         // the warp stays converged (warp-uniform schedule => descriptors in uniform registers), one elected lane issues;
         // a divergent `if (lane == 0)` makes the compiler wrap each tcgen05.mma in an elect/broadcast/branch loop
         {
-            const uint32_t idesc = sv::make_idesc_tf32(BM, p.bnt, 0, 0);
+            const uint32_t idesc = F16 ? sv::make_idesc_f16(BM, p.bnt, 0, 0, 0, 0) : sv::make_idesc_tf32(BM, p.bnt, 0, 0);
             const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint64_t desc_fixed = sv::make_smem_desc_sw128(0, 16, 1024);
             int stage = 0, it = 0;
@@ -342,7 +382,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
                     const uint64_t db_hi = da_lo + (uint64_t)(A_TILE_BYTES >> 4);
                     const uint64_t db_lo = db_hi + (uint64_t)(b_tile_bytes >> 4);
                     if (sv::elect_one()) {
-                        if (p.passes == 3) {
+                        if constexpr (F16) {   // 4 k16 steps of 32 bytes, three MMAs each (lo*hi + hi*lo + hi*hi)
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                sv::umma_f16(d_tmem, da_lo + 2 * k4, db_hi + 2 * k4, idesc, (uint32_t)(ks | k4));
+                                sv::umma_f16(d_tmem, da_hi + 2 * k4, db_lo + 2 * k4, idesc, 1u);
+                                sv::umma_f16(d_tmem, da_hi + 2 * k4, db_hi + 2 * k4, idesc, 1u);
+                            }
+                        } else if (p.passes == 3) {
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4) {
                                 sv::umma_tf32(d_tmem, da_lo + 2 * k4, db_hi + 2 * k4, idesc, (uint32_t)(ks | k4));
@@ -369,7 +416,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_igemm_kernel(const ConvP
     } else {
         // ------------------------------------------------------------------ B producer (one thread, TMA bulk)
         if (lane == 0) {
-            const uint32_t bytes = (uint32_t)(p.passes == 3 ? 2 * b_tile_bytes : b_tile_bytes);
+            const uint32_t bytes = (uint32_t)((F16 || p.passes == 3) ? 2 * b_tile_bytes : b_tile_bytes);
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -428,6 +475,31 @@ __global__ void conv_pack_weights_kernel(const float* __restrict__ W, int mode, 
     }
 }
 
+// fp16x3 forward variant: [ntile][kstage of 64 k][hi|lo][bnt rows][128 B], values scaled by 2^8; k = tap*cs + ci
+__global__ void conv_pack_weights_f16_kernel(const float* __restrict__ W, int co, int ci, int taps, int cs, int bnt, int ntiles,
+                                             int kstages, uint16_t* __restrict__ out) {
+    const size_t total = (size_t)ntiles * kstages * bnt * 64;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(idx & 7);
+        const int c = (int)((idx >> 3) & 7);
+        const int n = (int)((idx >> 6) % bnt);
+        const size_t blk = (idx >> 6) / bnt;  // ntile*kstages + ks
+        const int ks = (int)(blk % kstages);
+        const int nt = (int)(blk / kstages);
+        const int k = ks * 64 + c * 8 + e;
+        const int tap = k / cs, kc = k % cs;
+        const int nn = nt * bnt + n;
+        float val = 0.f;
+        if (tap < taps && nn < co && kc < ci) val = W[((size_t)nn * ci + kc) * taps + tap] * F16_WSCALE;
+        const __half h = __float2half_rn(val);
+        const __half l = __float2half_rn(val - __half2float(h));
+        uint16_t* base = out + blk * (size_t)(2 * bnt * 64);
+        const int pos = n * 64 + ((c ^ (n & 7)) << 3) + e;
+        base[pos] = __half_as_ushort(h);
+        base[bnt * 64 + pos] = __half_as_ushort(l);
+    }
+}
+
 void pick_tiles(int n_out, int* bnt, int* ntiles) {
     int nt = (n_out + 255) / 256;
     int per = (n_out + nt - 1) / nt;
@@ -451,10 +523,30 @@ extern "C" size_t selavi_conv_wpack_bytes(int n_out, int k_total) {
     return (size_t)nt * kstages * 2 * bnt * 128;
 }
 
+extern "C" size_t selavi_conv_wpack_bytes_f16(int n_out, int k_total) {
+    int bnt, nt;
+    pick_tiles(n_out, &bnt, &nt);
+    const int kstages = (k_total + 2 * BK - 1) / (2 * BK);
+    return (size_t)nt * kstages * 2 * bnt * 128;
+}
+
 extern "C" int selavi_conv_pack_weights(const float* W, int mode, int co, int ci, int taps, int cs, void* wpack,
                                         void* stream) {
     if (!W || !wpack || co <= 0 || ci <= 0 || taps <= 0 || (cs & 3)) return selavi_fail(-1, "conv_pack_weights: bad arguments");
     int bnt, nt;
+    if (mode == 2) {   // forward, fp16x3 operands (selavi_conv_gemm passes = 6)
+        if (cs & 7) return selavi_fail(-1, "conv_pack_weights: the fp16x3 variant needs channel strides in multiples of 8");
+        pick_tiles(co, &bnt, &nt);
+        const int kstages = (taps * cs + 2 * BK - 1) / (2 * BK);
+        const size_t total = (size_t)nt * kstages * bnt * 64;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        conv_pack_weights_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, co, ci, taps, cs, bnt, nt, kstages,
+                                                                               reinterpret_cast<uint16_t*>(wpack));
+        SV_CUDA_CHECK(cudaGetLastError(), "conv_pack_weights: launch");
+        return 0;
+    }
+    if (mode != 0 && mode != 1) return selavi_fail(-1, "conv_pack_weights: mode must be 0, 1 or 2");
     pick_tiles(mode == 0 ? co : ci, &bnt, &nt);
     const int kstages = (taps * cs + BK - 1) / BK;
     const size_t total = (size_t)nt * kstages * bnt * 32;
@@ -489,7 +581,9 @@ extern "C" int selavi_conv_gemm(const float* src, float* dst, const void* wpack,
     if (p.kt * p.kh * p.kw > MAX_TAPS) return selavi_fail(-1, "conv_gemm: too many taps");
     if (p.kt > 8 || p.kh > 8 || p.kw > 8) return selavi_fail(-1, "conv_gemm: kernel extent above 8 not supported");
     if ((p.st != 1 && p.st != 2) || (p.sh != 1 && p.sh != 2) || (p.sw != 1 && p.sw != 2)) return selavi_fail(-1, "conv_gemm: stride must be 1 or 2");
-    if (passes != 1 && passes != 3) return selavi_fail(-1, "conv_gemm: passes must be 1 or 3");
+    if (passes != 1 && passes != 3 && passes != 6) return selavi_fail(-1, "conv_gemm: passes must be 1, 3 (tf32) or 6 (fp16x3)");
+    const bool f16 = passes == 6;
+    if (f16 && (p.mode != 0 || (p.cs & 7))) return selavi_fail(-1, "conv_gemm: the fp16x3 variant is forward only, channel stride multiple of 8");
     if ((pro_scale == nullptr) != (pro_shift == nullptr)) return selavi_fail(-1, "conv_gemm: prologue needs scale and shift");
     const long long M = (long long)p.nb * p.td * p.hd * p.wd;
     if (M <= 0 || M > 0x7fffffffLL || (long long)p.nb * p.ts * p.hs * p.ws > 0x7fffffffLL) return selavi_fail(-1, "conv_gemm: bad pixel count");
@@ -497,11 +591,11 @@ extern "C" int selavi_conv_gemm(const float* src, float* dst, const void* wpack,
     pick_tiles(n_out, &p.bnt, &p.ntiles);
     // padded destination channels [n_out, cd) are written as exact zeros by the (zero) weight tile rows
     if (p.ntiles * p.bnt < p.cd) return selavi_fail(-1, "conv_gemm: cd exceeds the tiled channel range");
-    p.kstages = (p.kt * p.kh * p.kw * (p.cs >> 2) + 7) / 8;
+    p.kstages = f16 ? (p.kt * p.kh * p.kw * (p.cs >> 3) + 7) / 8 : (p.kt * p.kh * p.kw * (p.cs >> 2) + 7) / 8;
     p.m_tiles = (p.M + BM - 1) / BM;
     p.pro_relu = pro_relu;
     p.accumulate = accumulate;
-    p.passes = passes;
+    p.passes = f16 ? 3 : passes;
     uint32_t cols = 32;
     while ((int)cols < 2 * p.bnt) cols <<= 1;  // two accumulators (epilogue of tile i overlaps the MMAs of tile i+1)
     p.tmem_cols = cols;
@@ -513,14 +607,16 @@ extern "C" int selavi_conv_gemm(const float* src, float* dst, const void* wpack,
     if (stages < 2 && p.kstages > 1) return selavi_fail(-1, "conv_gemm: tile does not fit shared memory");
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + tail_bytes + 1024;
-    SV_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+    SV_CUDA_CHECK(f16 ? cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                      : cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                   "conv_gemm: cudaFuncSetAttribute");
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int total_tiles = p.m_tiles * p.ntiles;
     const int grid = total_tiles < sms ? total_tiles : sms;  // persistent: one CTA per SM
-    conv_igemm_kernel<<<grid, CONV_THREADS, smem, (cudaStream_t)stream>>>(p);
+    if (f16) conv_igemm_kernel<true><<<grid, CONV_THREADS, smem, (cudaStream_t)stream>>>(p);
+    else conv_igemm_kernel<false><<<grid, CONV_THREADS, smem, (cudaStream_t)stream>>>(p);
     SV_CUDA_CHECK(cudaGetLastError(), "conv_gemm: launch");
     return 0;
 }

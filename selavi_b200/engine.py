@@ -24,6 +24,9 @@ PASSES = int(os.environ.get("SELAVI_MMA_PASSES", "3"))
 # backward (data + weight gradients): "bf16x3" (default; gradient planes written as bf16 hi/lo by the BN-backward
 # kernel, cp.async-fed tcgen05 kind::f16 kernels, measured 4e-6 per-layer error) or "tf32x3" (register-staged loaders)
 BWD = os.environ.get("SELAVI_BWD", "bf16x3")
+# forward of the convolutions the tap-reuse kernel does not cover (strided, 7x7, 1x1): "fp16x3" (default; fp16 hi/lo operands
+# like conv_halo.cu, half the stages / shared-memory bytes / MMAs of tf32x3) or "tf32x3"
+IGEMM_FWD = os.environ.get("SELAVI_IGEMM_FWD", "fp16x3")
 
 
 def _stream():
@@ -162,7 +165,9 @@ class TowerRunner:
         geom = _geom_of(conv, nb, (t, h, w))
         plan = ops.halo_plan(geom) if PASSES == 3 else None
         halo = plan is not None
-        wp = _packed(conv, geom, ("halo", plan[1], plan[2]) if halo else 0)
+        f16 = PASSES == 3 and IGEMM_FWD == "fp16x3"
+        wp = _packed(conv, geom, ("halo", plan[1], plan[2]) if halo else (2 if f16 else 0))
+        igemm_passes = 6 if f16 else PASSES
         dev = x.device
         cs = geom.cos
         scale = torch.empty(cs, dtype=torch.float32, device=dev)
@@ -173,7 +178,7 @@ class TowerRunner:
             if halo:
                 z = ops.conv_forward_halo(x, wp, geom, scale=act.scale, shift=act.shift, relu=act.relu, stats=stats)
             else:
-                z = ops.conv_forward(x, wp, geom, scale=act.scale, shift=act.shift, relu=act.relu, stats=stats, passes=PASSES)
+                z = ops.conv_forward(x, wp, geom, scale=act.scale, shift=act.shift, relu=act.relu, stats=stats, passes=igemm_passes)
             sums = torch.empty(2 * cs, dtype=torch.float64, device=dev)
             _lib.check(lib.selavi_bn_reduce_partials(_lib.ptr(stats), stats.shape[0], stats.shape[2], cs, _lib.ptr(sums),
                                                      _stream()), "selavi_bn_reduce_partials")
@@ -201,7 +206,7 @@ class TowerRunner:
             if halo:
                 z = ops.conv_forward_halo(x, wp, geom, scale=act.scale, shift=act.shift, relu=act.relu, stats=None)
             else:
-                z = ops.conv_forward(x, wp, geom, scale=act.scale, shift=act.shift, relu=act.relu, stats=None, passes=PASSES)
+                z = ops.conv_forward(x, wp, geom, scale=act.scale, shift=act.shift, relu=act.relu, stats=None, passes=igemm_passes)
             _lib.check(lib.selavi_bn_eval_affine(_lib.ptr(bn.weight), _lib.ptr(bn.bias), _lib.ptr(bn.running_mean),
                                                  _lib.ptr(bn.running_var), bn.eps, geom.co, cs, _lib.ptr(scale),
                                                  _lib.ptr(shift), _stream()), "selavi_bn_eval_affine")

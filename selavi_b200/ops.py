@@ -121,8 +121,9 @@ def pack_weights(w, geom, mode, out=None):
     if not (w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()):
         raise ValueError("weight must be a contiguous fp32 CUDA tensor")
     lib = _lib.lib()
-    n_out, cs = (geom.co, geom.cis) if mode == 0 else (geom.ci, geom.cos)
-    nbytes = lib.selavi_conv_wpack_bytes(n_out, geom.taps * cs)
+    n_out, cs = (geom.ci, geom.cos) if mode == 1 else (geom.co, geom.cis)
+    # mode 0 / 1: tf32 hi/lo tiles of the forward / data-gradient implicit GEMM; mode 2: fp16 hi/lo tiles of the forward
+    nbytes = lib.selavi_conv_wpack_bytes_f16(n_out, geom.taps * cs) if mode == 2 else lib.selavi_conv_wpack_bytes(n_out, geom.taps * cs)
     if out is None:
         out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
     elif out.numel() != nbytes:
@@ -236,7 +237,7 @@ def conv_forward(x, wpack, geom, out=None, scale=None, shift=None, relu=False, s
     if out is None:
         out = torch.empty(geom.out_shape(), dtype=torch.float32, device=x.device)
     _chk(out, geom.out_shape(), "out")
-    with _Guard(x.device), _Prof("conv_fwd", geom, "conv_igemm_kernel[fwd tf32x3]"):
+    with _Guard(x.device), _Prof("conv_fwd", geom, "conv_igemm_kernel[fwd fp16x3]" if passes == 6 else "conv_igemm_kernel[fwd tf32x3]"):
         _lib.check(_lib.lib().selavi_conv_gemm(_lib.ptr(x), _lib.ptr(out), _lib.ptr(wpack), geom.arr(0), _lib.ptr(scale),
                                                _lib.ptr(shift), 1 if relu else 0, _lib.ptr(stats), 0, passes,
                                                _lib.stream_ptr()), "selavi_conv_gemm(fwd)")

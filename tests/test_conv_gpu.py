@@ -43,20 +43,22 @@ def _rel(a, b):
 @pytest.mark.parametrize("name", sorted(LAYERS))
 # passes=3 (tf32x3): operand error ~2^-21; the tensor core adds each K=8 partial product into the fp32
 # accumulator with truncation, so the error grows ~n_mma * 2^-25 (measured 8e-7 at K=64, 4e-6 at K=576).
-@pytest.mark.parametrize("passes,tol", [(3, 5e-5), (1, 2e-3)])
+# passes=6 (fp16x3, the default forward of the strided / 7x7 / 1x1 convolutions): fp16 hi/lo operands, same accuracy class.
+@pytest.mark.parametrize("passes,tol", [(6, 5e-5), (3, 5e-5), (1, 2e-3)])
 def test_conv_forward(cuda_device, name, passes, tol):
     from selavi_b200 import ops
     x, w, geom, (s, p) = _mk(name, cuda_device)
     ref = F.conv3d(x.double(), w.double(), None, s, p)
-    y = ops.conv_forward(ops.to_channels_last(x), ops.pack_weights(w, geom, 0), geom, passes=passes)
+    y = ops.conv_forward(ops.to_channels_last(x), ops.pack_weights(w, geom, 2 if passes == 6 else 0), geom, passes=passes)
     assert y[..., geom.co:].abs().max().item() == 0 if geom.cos > geom.co else True
     err = _rel(ops.from_channels_last(y, geom.co), ref)
     print(f"{name} fwd passes={passes} rel={err:.3e}")
     assert err < tol
 
 
-@pytest.mark.parametrize("name", ["v_l1_spatial", "v_stem3_t", "a_l2_3x3_s2", "ragged_m"])
-def test_conv_forward_fused_bn_relu_prologue_and_stats(cuda_device, name):
+@pytest.mark.parametrize("passes", [6, 3])
+@pytest.mark.parametrize("name", ["v_l1_spatial", "v_stem3_t", "a_l2_3x3_s2", "ragged_m", "v_l2_temporal_s2", "v_stem0_7x7"])
+def test_conv_forward_fused_bn_relu_prologue_and_stats(cuda_device, name, passes):
     """prologue = train-mode BN(+ReLU) of the previous layer applied on the fly; epilogue = per-channel stats."""
     from selavi_b200 import ops
     x, w, geom, (s, p) = _mk(name, cuda_device)
@@ -66,8 +68,8 @@ def test_conv_forward_fused_bn_relu_prologue_and_stats(cuda_device, name):
     xn = torch.relu(x.double() * scale[:geom.ci].double().view(1, -1, 1, 1, 1) + shift[:geom.ci].double().view(1, -1, 1, 1, 1))
     ref = F.conv3d(xn, w.double(), None, s, p)
     stats = ops.stats_buffer(geom, cuda_device)
-    y = ops.conv_forward(ops.to_channels_last(x), ops.pack_weights(w, geom, 0), geom, scale=scale, shift=shift, relu=True,
-                         stats=stats)
+    y = ops.conv_forward(ops.to_channels_last(x), ops.pack_weights(w, geom, 2 if passes == 6 else 0), geom, scale=scale, shift=shift,
+                         relu=True, stats=stats, passes=passes)
     assert _rel(ops.from_channels_last(y, geom.co), ref) < 5e-5
     tot = stats.double().sum(0)[:, :geom.co]
     # fp32 per-tile partial sums: tolerance relative to the L1 / L2 mass of the channel

@@ -28,9 +28,13 @@ def _oracle_npz(path):
         loss.backward()
         grads[dtype] = {n: p.grad.detach().double().numpy() for n, p in m.named_parameters()}
         out["loss64" if dtype == torch.float64 else "loss32"] = float(loss)
+    num = den = 0.0
     for n, g64 in grads[torch.float64].items():
         out["grad64/" + n] = g64
         out["err32/" + n] = np.linalg.norm(grads[torch.float32][n] - g64) / (np.linalg.norm(g64) + 1e-30)
+        num += float(((grads[torch.float32][n] - g64) ** 2).sum())
+        den += float((g64 ** 2).sum())
+    out["global_err32"] = (num / den) ** 0.5     # the fp32 reference's own error over the concatenated gradient
     np.savez(path, **out)
 
 
