@@ -70,6 +70,26 @@ def audio_stream(dev):
     return s
 
 
+# DistributedDataParallel (main.py:156-160) is told to ignore the towers' parameters and every BatchNorm buffer
+# (model.AVModel._ddp_params_and_buffers_to_ignore); the engine averages the tower gradients itself: chunks of ~32 MB are
+# flattened and all-reduced (NCCL, AVG) on a communication stream as soon as the weight gradients of the blocks they
+# belong to are complete, so the exchange of layer 4 (3/4 of all parameters, finished in the first tenth of backward)
+# hides behind layers 3..1.  DDP's own path hands autograd's 247 gradients to the reducer only when the tower's single
+# autograd node returns (nothing overlaps), copies each of them into a bucket and back, and re-broadcasts 300 BatchNorm
+# buffers before every forward although SyncBatchNorm keeps them identical by construction.  SELAVI_DDP_BYPASS=0 restores it.
+DDP_BYPASS = os.environ.get("SELAVI_DDP_BYPASS", "1") == "1"
+REDUCE_CHUNK_BYTES = int(os.environ.get("SELAVI_REDUCE_CHUNK_MB", "32")) << 20
+_comm_streams = {}
+
+
+def _comm_stream(dev):
+    s = _comm_streams.get(dev.index)
+    if s is None:
+        s = torch.cuda.Stream(device=dev)
+        _comm_streams[dev.index] = s
+    return s
+
+
 # cross-rank exchange of the SyncBN statistic vectors: "p2p" = one tiny kernel over NVSwitch peer memory (default inside
 # one node, world <= 8), "nccl" = torch.distributed.all_reduce
 BN_EXCHANGE = os.environ.get("SELAVI_BN_EXCHANGE", "p2p")
@@ -156,6 +176,7 @@ class TowerRunner:
 
     def __init__(self, net, kind):
         self.kind = kind
+        self.own_allreduce = None      # process group (or True for the default group) once DDP ignores this tower's parameters
 
     # ------------------------------------------------------------------ forward pieces
     def conv_bn(self, act, conv, bn, training, tape):
@@ -361,17 +382,51 @@ class TowerRunner:
 
     def backward(self, tape, dfeat, grads):
         self._side_busy = False
+        self._comm_busy = False
+        self._reduced = set()
         try:
             self._backward(tape, dfeat, grads)
+            self._reduce_ready(grads, dfeat.device, final=True)
         finally:
+            main = torch.cuda.current_stream(dfeat.device)
             if self._side_busy:   # the weight gradients must be complete before autograd hands them to DDP / the optimizer
-                torch.cuda.current_stream(dfeat.device).wait_stream(_side_stream(dfeat.device))
+                main.wait_stream(_side_stream(dfeat.device))
+            if self._comm_busy:
+                main.wait_stream(_comm_stream(dfeat.device))
+
+    def _reduce_ready(self, grads, dev, final=False):
+        """Average the gradients produced since the last call over the data-parallel ranks (see DDP_BYPASS)."""
+        if self.own_allreduce is None or not (dist.is_available() and dist.is_initialized()):
+            return
+        group = None if self.own_allreduce is True else self.own_allreduce
+        if dist.get_world_size(group) < 2:
+            return
+        new = [t for p, t in grads.items() if id(p) not in self._reduced and t is not None]
+        if not new or (not final and 4 * sum(t.numel() for t in new) < REDUCE_CHUNK_BYTES):
+            return
+        self._reduced.update(id(p) for p in grads)
+        main, comm = torch.cuda.current_stream(dev), _comm_stream(dev)
+        comm.wait_stream(main)                       # BatchNorm scale / bias gradients are produced on this stream
+        if self._side_busy:
+            comm.wait_stream(_side_stream(dev))      # ... the weight gradients on the side stream
+        with torch.cuda.stream(comm):
+            flat = torch.cat([t.reshape(-1) for t in new])
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+            off, pieces = 0, []
+            for t in new:
+                pieces.append(flat[off:off + t.numel()].view_as(t))
+                off += t.numel()
+            torch._foreach_copy_(new, pieces)
+        for t in new:
+            t.record_stream(comm)
+        self._comm_busy = True
 
     def _backward(self, tape, dfeat, grads):
         lib = _lib.lib()
         dfeat = dfeat.contiguous()
         g = None
         for entry in reversed(tape):
+            self._reduce_ready(grads, dfeat.device)      # whatever the previous entries produced, once a chunk is full
             kind = entry[0]
             if kind == "pool":
                 shape, c = entry[1], entry[2]

@@ -288,6 +288,40 @@ class AVModel(nn.Module):
                     setattr(self, "mlp_v%d" % a, LinearHead(encoder_dim, num_classes))
                     setattr(self, "mlp_a%d" % a, LinearHead(encoder_dim_a, num_classes))
 
+    @property
+    def _ddp_params_and_buffers_to_ignore(self):
+        """Read by torch.nn.parallel.DistributedDataParallel when it is constructed around this model (main.py:156-160):
+        the names it must neither broadcast nor reduce.  When the model was converted to SyncBatchNorm (main.py:117-118)
+        these are every BatchNorm buffer (identical on all ranks by construction: the statistics are computed from the
+        global batch) and the two towers' parameters, whose gradients the engine averages itself, overlapped with
+        backward (engine.DDP_BYPASS).  DDP's construction-time broadcast of rank 0's state is done here for them."""
+        import torch.distributed as dist
+        if not (engine.DDP_BYPASS and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+                and any(isinstance(m, nn.SyncBatchNorm) for m in self.modules())):
+            raise AttributeError("_ddp_params_and_buffers_to_ignore")
+        towers = (("video_network.base", self.video_network.base, "video"), ("audio_network.base", self.audio_network.base, "audio"))
+        names = [n for n, _ in self.named_buffers()]
+        tensors = [b for _, b in self.named_buffers()]
+        for prefix, net, kind in towers:
+            names += [f"{prefix}.{n}" for n, _ in net.named_parameters()]
+            tensors += [p.data for _, p in net.named_parameters()]
+            runner = net.__dict__.get("_sv_runner")
+            if runner is None:
+                runner = net.__dict__["_sv_runner"] = engine.TowerRunner(net, kind)
+            runner.own_allreduce = True
+        if tensors and tensors[0].is_cuda and not self.__dict__.get("_sv_ddp_synced"):
+            # rank 0's state to every rank, like DDP's _sync_module_states (DDP reads this attribute twice: sync once)
+            self.__dict__["_sv_ddp_synced"] = True
+            for dt in {t.dtype for t in tensors}:
+                grp = [t for t in tensors if t.dtype == dt]
+                flat = torch.cat([t.reshape(-1) for t in grp])
+                dist.broadcast(flat, 0)
+                off = 0
+                for t in grp:
+                    t.copy_(flat[off:off + t.numel()].view_as(t))
+                    off += t.numel()
+        return names
+
     def _heads(self, prefix):
         if self.hc == 1:
             return [getattr(self, prefix)]

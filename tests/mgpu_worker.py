@@ -5,8 +5,7 @@
 
 1. row-sharded Sinkhorn-Knopp (in-kernel NVSwitch exchange of the column sums) == CPU oracle on the full matrix, and the
    NCCL gather fallback (`optimize_L_sk_gathered`) gives the same labels
-2. DDP + SyncBN train step on a rank-sharded batch AND the single-GPU step on the full batch: against each other (2e-3 per
-   parameter) and BOTH against the float64 CPU oracle of the full batch (global max(5e-3, 4 x the fp32 reference's own
+2. DDP + SyncBN train step on a rank-sharded batch AND the single-GPU step on the full batch: against each other and BOTH against the float64 CPU oracle of the full batch (global max(5e-3, 4 x the fp32 reference's own
    error); per parameter max(5e-2, 8 x the reference's own error) — see the comment at the comparison)
 3. row-sharded dataset sweep + label assignment (`get_cluster_assignments_gpu`, cfg-4 flow: match, ind_groups = 2) ==
    CPU bookkeeping oracle, identical on every rank
@@ -119,9 +118,26 @@ def main():
     l_ddp = step(ddp, torch.from_numpy(video[sl]).to(dev), torch.from_numpy(spec[sl]).to(dev), torch.from_numpy(labels[sl]).to(dev))
     dist.all_reduce(l_ddp)
     l_ddp /= world
+    # the same step with DistributedDataParallel's stock gradient path (engine.DDP_BYPASS off: DDP reduces every parameter
+    # and broadcasts the buffers itself): identical forward, so the gradients must agree to all-reduce rounding
+    from selavi_b200 import engine
+    engine.DDP_BYPASS = False
+    stock_m = torch.nn.SyncBatchNorm.convert_sync_batchnorm(build_model(factory)).to(dev).train()
+    assert not hasattr(stock_m, "_ddp_params_and_buffers_to_ignore")
+    stock = torch.nn.parallel.DistributedDataParallel(stock_m, device_ids=[local], find_unused_parameters=True)
+    step(stock, torch.from_numpy(video[sl]).to(dev), torch.from_numpy(spec[sl]).to(dev), torch.from_numpy(labels[sl]).to(dev))
+    engine.DDP_BYPASS = True
+    g_ddp = dict(ddp_m.named_parameters())
+    worst_stock = max((float((p.grad - g_ddp[n].grad).norm() / (p.grad.norm() + 1e-30)), n) for n, p in stock_m.named_parameters())
+    say(f"engine-side gradient averaging vs stock DDP reducer: worst parameter {worst_stock[0]:.2e} ({worst_stock[1]}); "
+        f"towers ignored by DDP: {len(ddp.parameters_to_ignore)} names")
+    ok &= worst_stock[0] < 1e-5 and len(ddp.parameters_to_ignore) > 300 and len(stock.parameters_to_ignore) == 0
     # Three comparisons, per parameter and over the concatenated gradient ("global"):
     #   (a) DDP + SyncBN on the rank-sharded batch  vs  the same kernels on one GPU with the full batch: only the summation
-    #       order of the BatchNorm statistics / gradient all-reduce differs, bar 2e-3 per parameter;
+    #       order of the BatchNorm statistics differs (1e-7 relative), but on this ill-conditioned toy step even that can
+    #       flip a ReLU at the top of the towers: measured 1.7e-5 (no flip) or 1.2e-2 (one flip) depending on the kernel
+    #       version, so the bar is the same 5e-2 as against float64.  The EXACT check of the multi-GPU plumbing is the
+    #       bit-identity of the engine-side gradient averaging with DDP's stock reducer above;
     #   (b), (c) each of the two vs the float64 CPU oracle.  The clips are tiny (8 x 3x4x64x64: layer 4 holds 32 values per
     #       channel, BatchNorm1d sees 8 rows), so ONE ReLU whose pre-activation sits within the forward's 1e-4 rounding of
     #       zero changes a BatchNorm-bias gradient by percents (the fp32 reference, 10x more accurate in the forward, flips
@@ -153,7 +169,7 @@ def main():
     loss64 = float(gold["loss64"])
     loss_ok = abs(float(l_ddp) - loss64) < 1e-4 * abs(loss64) and abs(float(l_single) - loss64) < 1e-4 * abs(loss64)
     gbar = max(5e-3, 4 * float(gold["global_err32"]))
-    grads_ok = rows[0][0] <= 1.0 and glob["ddp"] < gbar and glob["single"] < gbar and worst_pair[0] < 2e-3
+    grads_ok = rows[0][0] <= 1.0 and glob["ddp"] < gbar and glob["single"] < gbar and worst_pair[0] < 5e-2
     say(f"DDP+SyncBN: loss ddp {float(l_ddp):.6f} single {float(l_single):.6f} fp64 oracle {loss64:.6f}; global gradient error vs fp64: "
         f"ddp {glob['ddp']:.2e} single {glob['single']:.2e} (reference fp32 {float(gold['global_err32']):.2e}, bar {gbar:.2e}); ddp vs single: global {glob['pair']:.2e}, worst parameter "
         f"{worst_pair[0]:.2e} ({worst_pair[1]})")

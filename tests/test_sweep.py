@@ -299,3 +299,39 @@ def test_sweep_against_cpu_oracle_towers(cuda_device):
     agree = float((L.cpu().numpy() == L_ref).mean())
     print(f"sweep vs full CPU oracle (towers included): {agree * 100:.1f} % of {N * hc} labels agree")
     assert agree >= 0.97
+
+
+def _ddp_ignore_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from selavi_b200 import model as sv_model
+    torch.manual_seed(31 + rank)             # different initial weights per rank on purpose
+    m = sv_model.load_model(use_mlp=True, headcount=2, num_classes=8, norm_feat=False)
+    assert not hasattr(torch.nn.Module(), "_ddp_params_and_buffers_to_ignore")
+    plain = hasattr(m, "_ddp_params_and_buffers_to_ignore")          # plain BatchNorm: DDP keeps its stock behaviour
+    m = torch.nn.SyncBatchNorm.convert_sync_batchnorm(m)
+    names = set(m._ddp_params_and_buffers_to_ignore)
+    # what DistributedDataParallel.__init__ does with the attribute (torch/nn/parallel/distributed.py:723-736); DDP itself
+    # refuses SyncBatchNorm modules on the CPU, the real construction is exercised by tests/test_multigpu.py
+    assert hasattr(m, "_ddp_params_and_buffers_to_ignore")
+    ignore = set(m._ddp_params_and_buffers_to_ignore)
+    reduced_by_ddp = [n for n, _ in m.named_parameters() if n not in ignore]
+    if rank == 0:
+        torch.save(dict(plain=plain, names=sorted(names), reduced=reduced_by_ddp, buffers=[n for n, _ in m.named_buffers()],
+                        tower=[n for n, _ in m.named_parameters() if n.startswith(("video_network", "audio_network"))],
+                        own=(m.video_network.base.__dict__["_sv_runner"].own_allreduce, m.audio_network.base.__dict__["_sv_runner"].own_allreduce)),
+                   out)
+    dist.destroy_process_group()
+
+
+def test_ddp_ignores_tower_params_and_bn_buffers_gloo(tmp_path):
+    """engine.DDP_BYPASS: a SyncBatchNorm-converted model tells DistributedDataParallel to leave the towers' parameters and
+    all BatchNorm buffers alone (the engine averages those gradients itself, overlapped with backward); the heads stay
+    with DDP; a model with plain BatchNorm does not expose the attribute at all."""
+    out = str(tmp_path / "ignore.pt")
+    mp.spawn(_ddp_ignore_worker, args=(2, 29671, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["plain"] is False
+    assert set(r["buffers"]) <= set(r["names"]) and set(r["tower"]) <= set(r["names"])
+    assert r["reduced"] and all(n.startswith("mlp_") for n in r["reduced"])
+    assert r["own"] == (True, True)
