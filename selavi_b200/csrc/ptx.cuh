@@ -54,6 +54,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the thread is parked by the hardware until the phase completes or the time is up,
+// instead of burning issue slots in a spin loop (ncu on sk_kernel: half of all issued instructions were try_wait spins,
+// and the spinning producer slowed the three consumer warps that share its scheduler)
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
