@@ -30,8 +30,23 @@ sys.path.insert(0, ROOT)
 
 METRIC = "clips/sec (video+audio fwd/bwd + SK assign)"
 CFG = dict(batch=16, T=32, HW=112, spec_T=200, K=309, hc=10)
+# BASELINE.json configs: [1] (default, the configuration the metric is quoted on), [2] Kinetics-400 shape, [3] AVE shape with
+# `match` and ind_groups=2; the train step differs only in K, the assignment phase in K, N and the head alignment
+CONFIGS = {"cfg2": dict(idx=1, K=309, N=170752, match=False, ind_groups=1, name="VGG-Sound shape"),
+           "cfg3": dict(idx=2, K=400, N=230976, match=False, ind_groups=1, name="Kinetics-400 shape"),
+           "cfg4": dict(idx=3, K=28, N=3328, match=True, ind_groups=2, name="AVE shape, match=True, ind_groups=2")}
 WORKLOAD = ("configs[1]: train step (video R(2+1)D-18 + audio ResNet-9 fwd/bwd, 20 MLP heads, CE, SGD), per-GPU batch 16, "
             "clips 3x32x112x112, spectrograms 1x257x200, K=309, 10 heads")
+
+
+def select_config(name):
+    global WORKLOAD, SK_DATASET_N
+    c = CONFIGS[name]
+    CFG["K"] = c["K"]
+    SK_DATASET_N = c["N"]
+    WORKLOAD = (f"configs[{c['idx']}] ({c['name']}): train step (video R(2+1)D-18 + audio ResNet-9 fwd/bwd, 20 MLP heads, CE, SGD), "
+                f"per-GPU batch 16, clips 3x32x112x112, spectrograms 1x257x200, K={c['K']}, 10 heads")
+    return c
 # SURVEY §8d / BASELINE.md §3: algorithmic conv+linear FLOPs of one train step per sample (3x fwd - input dgrads)
 FLOP_PER_SAMPLE_STEP = 490.3e9
 # the reference's SK schedule (opt.py:71,88): nopts = 100 label optimisations over epochs = 100, i.e. on average one
@@ -231,7 +246,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))   # a hang fails fast
         dist.barrier()
     _lib.lib()
     pk = peaks()
@@ -502,11 +518,22 @@ def run_ours(args):
         kw = dict(world=world, rank=rank, peer_sum=comm.sum.peer_ptrs, peer_flag=comm.flag.peer_ptrs) if comm else {}
         iters_seen = []
 
+        match_s = [0.0]
+
         def assign_all():
             with torch.no_grad():
                 for h in range(hc):
                     lv = getattr(model, f"mlp_v{h}").forward(F_v)
                     la = getattr(model, f"mlp_a{h}").forward(F_a)
+                    if args.cfg["match"]:      # first SK call of cfg-4: align the audio head to the video head first
+                        import types
+                        from selavi_b200.sk_utils import match_order
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        match_order(types.SimpleNamespace(rank=rank), lv, la, list(getattr(model, f"mlp_a{h}").modules())[-1], logits=True)
+                        torch.cuda.synchronize()
+                        match_s[0] += time.perf_counter() - t0
+                        la = getattr(model, f"mlp_a{h}").forward(F_a)
                     PSh = softmax_product(lv, la)
                     if comm:
                         comm.reset()
@@ -514,15 +541,20 @@ def run_ours(args):
             iters_seen.append(int(ws2.iters.item()))
 
         assign_all()
+        match_s[0] = 0.0
         ms_as = timed(assign_all, 1)
         model.train()
         assign = {"seconds": ms_as * 1e-3, "heads": hc, "rows": n_rows * world, "K": K, "sk_iters_last_head": iters_seen[-1],
+                  **({"match_order_seconds": match_s[0], "ind_groups": args.cfg["ind_groups"],
+                      "note": "match_order = K x K L1 cost-matrix kernel + host hill-climb (np.random stream of the reference); with "
+                              "ind_groups=2 the reference sweeps the dataset twice (see 'incl_sk')"} if args.cfg["match"] else {}),
                   "what": "10 x (2 MLP heads on [N,512] features, float64 softmax product, Sinkhorn-Knopp to convergence, argmax)"}
         del F_v, F_a, ws2
         train_cps = B * world / (ms_step * 1e-3)
-        per_clip = 1.0 / train_cps + (SK_NOPTS / SK_EPOCHS) * (1.0 / sweep_cps + ms_as * 1e-3 / SK_DATASET_N)
+        per_clip = 1.0 / train_cps + (SK_NOPTS / SK_EPOCHS) * (args.cfg["ind_groups"] / sweep_cps + ms_as * 1e-3 / SK_DATASET_N)
         incl = {"value": 1.0 / per_clip, "unit": "clips/s",
-                "formula": "1 / (1/train + (nopts/epochs) * (1/sweep + assign_seconds/N)), nopts=100, epochs=100, N=170752 (opt.py:71,88)"}
+                "formula": f"1 / (1/train + (nopts/epochs) * (ind_groups/sweep + assign_seconds/N)), nopts=100, epochs=100, "
+                           f"N={SK_DATASET_N}, ind_groups={args.cfg['ind_groups']} (opt.py:71,88,102)"}
     except Exception as e:  # noqa: BLE001
         sweep = sweep or {"error": repr(e)[:300]}
         model.return_features = False
@@ -598,12 +630,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=CFG["batch"], help="per-GPU batch (configs[1]: 16)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_gpu"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json configs[1] (default) / [2] / [3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--library-baseline", action="store_true", help="also at N > 1 (default: N = 1 only)")
     ap.add_argument("--no-fast-mode", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=330.0, help="--impl reference: wall-clock cap of the timed steps")
     args = ap.parse_args()
+    args.cfg = select_config(args.config)
     if args.impl == "reference":
         run_reference(args)
     elif args.impl == "reference_gpu":

@@ -309,10 +309,12 @@ class AVModel(nn.Module):
             if runner is None:
                 runner = net.__dict__["_sv_runner"] = engine.TowerRunner(net, kind)
             runner.own_allreduce = True
-        if tensors and tensors[0].is_cuda and not self.__dict__.get("_sv_ddp_synced"):
+        if tensors and not self.__dict__.get("_sv_ddp_synced"):
             # rank 0's state to every rank, like DDP's _sync_module_states (DDP reads this attribute twice: sync once)
             self.__dict__["_sv_ddp_synced"] = True
-            for dt in {t.dtype for t in tensors}:
+            # (dtypes in a FIXED order: a set's iteration order differs between processes, and a rank that broadcasts its
+            # int64 counters while the others broadcast fp32 weights hangs the communicator — seen at 4 ranks)
+            for dt in sorted({t.dtype for t in tensors}, key=str):
                 grp = [t for t in tensors if t.dtype == dt]
                 flat = torch.cat([t.reshape(-1) for t in grp])
                 dist.broadcast(flat, 0)

@@ -52,7 +52,7 @@ def test_multi_gpu_parity(cuda_device, oracle_file, world):
         pytest.skip(f"needs {world} visible GPUs, found {torch.cuda.device_count()}")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29530 + world), os.path.join(ROOT, "tests", "mgpu_worker.py"), oracle_file]
-    res = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    res = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=420)
     print(res.stdout[-6000:])
     log_dir = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(log_dir):

@@ -316,6 +316,12 @@ def _ddp_ignore_worker(rank, world, port, out):
     assert hasattr(m, "_ddp_params_and_buffers_to_ignore")
     ignore = set(m._ddp_params_and_buffers_to_ignore)
     reduced_by_ddp = [n for n, _ in m.named_parameters() if n not in ignore]
+    # the ignored tensors were synchronised to rank 0's values here (DDP's own construction-time broadcast skips them)
+    probe = torch.cat([m.video_network.base.stem[0].weight.detach().reshape(-1)[:64],
+                       m.audio_network.base.layer4[0].conv2.weight.detach().reshape(-1)[:64]])
+    gathered = [torch.empty_like(probe) for _ in range(world)]
+    dist.all_gather(gathered, probe)
+    assert all(torch.equal(g, gathered[0]) for g in gathered)
     if rank == 0:
         torch.save(dict(plain=plain, names=sorted(names), reduced=reduced_by_ddp, buffers=[n for n, _ in m.named_buffers()],
                         tower=[n for n, _ in m.named_parameters() if n.startswith(("video_network", "audio_network"))],
