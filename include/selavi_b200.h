@@ -102,6 +102,9 @@ int selavi_split_bf16(const float* x, const float* scale, const float* shift, in
 int selavi_conv_wgrad_bf16(const float* src, const void* z_hi, const void* z_lo, float* dW, const int* geom, int ci_real,
                            const float* pro_scale, const float* pro_shift, int pro_relu, void* workspace, int accumulate,
                            int passes, void* stream);
+/* same with the conv input already split into bf16 hi/lo planes [pixels_in, cs] (act_hi/act_lo of selavi_bn_bwd_apply) */
+int selavi_conv_wgrad_bf16_planes(const void* a_hi, const void* a_lo, const void* z_hi, const void* z_lo, float* dW,
+                                  const int* geom, int ci_real, void* workspace, int accumulate, int passes, void* stream);
 /* host-only: tiling of the bf16x3 weight gradient selavi_conv_wgrad(_bf16) will use for this geometry: 128-row tiles of the
  * flattened (tap, channel) rows, column tile width / count, row tiles per CTA (they share every dz stage), the largest number
  * of split-K slices a group of row tiles gets (slices are dealt in proportion to a group's row tiles; one wave of CTAs in
@@ -144,7 +147,10 @@ int selavi_conv_halo_dgrad(const void* z_hi, const void* z_lo, float* dx, const 
  *   bwd_reduce:      sums [2][cs] = (sum g, sum g*zhat), g masked by the following ReLU:
  *                    mask_mode 0 none, 1 act>0 (materialised block output), 2 z*scale+shift>0
  *   bwd_apply:       dz = scale*(g - sum_g/count - zhat*sum_gz/count) as fp32 (dz, nullable) and/or as bf16 hi/lo
- *                    planes (dz_hi/dz_lo, nullable) for the bf16x3 gradient kernels; optional gres (+)= masked g
+ *                    planes (dz_hi/dz_lo, nullable) for the bf16x3 gradient kernels; optional gres (+)= masked g;
+ *                    optional act_hi/act_lo (nullable, mask_mode 1 or 2): bf16 hi/lo planes of this unit's OUTPUT
+ *                    activation (mode 1: act, mode 2: relu(z*scale+shift)) = the input operand of the weight gradient
+ *                    of the convolution that consumed it (selavi_conv_wgrad_bf16_planes): saves that split pass
  */
 int selavi_bn_reduce_partials(const float* partial, int tiles, int ctot, int cs, double* sums, void* stream);
 int selavi_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
@@ -161,7 +167,7 @@ int selavi_bn_bwd_reduce(const float* g, const float* z, const float* act, int m
 int selavi_bn_bwd_apply(const float* g, const float* z, const float* act, int mask_mode, const float* scale,
                         const float* shift, const float* mean, const float* invstd, const double* sums, double count,
                         long long M, int cs, float* dz, float* gres, int gres_accumulate, void* dz_hi, void* dz_lo,
-                        void* stream);
+                        void* act_hi, void* act_lo, void* stream);
 int selavi_relu_bwd(const float* g, const float* act, float* out, long long n, int accumulate, void* stream);
 /* MaxPool2d(3,2,1) over relu(z*scale+shift) (tv:resnet.py:268-271) and its gradient wrt that activation */
 int selavi_maxpool3x3s2_fwd(const float* z, const float* scale, const float* shift, float* out, int nb, int h, int w,

@@ -51,7 +51,10 @@ SIGNATURES = {
     "selavi_bn_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_ll,
                                      c_int, c_void_p, c_void_p, c_void_p]),
     "selavi_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                    c_double, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+                                    c_double, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
+    "selavi_conv_wgrad_bf16_planes": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                              c_int, c_void_p]),
     "selavi_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "selavi_conv_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                        c_void_p, c_int, c_int, c_void_p]),
@@ -115,7 +118,7 @@ KERNELS_PER_CALL = {
     "selavi_sgd_step": 1, "selavi_sgd_step_host": 6, "selavi_bgemm": 1, "selavi_heads_bn_stats": 1, "selavi_heads_bn_finalize": 1,
     "selavi_heads_bn_eval_affine": 1, "selavi_heads_act": 1, "selavi_heads_bn_bwd_reduce": 1,
     "selavi_heads_bn_bwd_apply": 1, "selavi_heads_sum_masked": 1, "selavi_heads_colsum": 1, "selavi_ce_loss": 2,
-    "selavi_mel_logfbank": 1, "selavi_split_bf16": 1, "selavi_p2p_allreduce_f64": 1, "selavi_conv_wgrad_bf16": 3,
+    "selavi_mel_logfbank": 1, "selavi_split_bf16": 1, "selavi_p2p_allreduce_f64": 1, "selavi_conv_wgrad_bf16": 3, "selavi_conv_wgrad_bf16_planes": 2,
     "selavi_dgrad_pack_weights": 1, "selavi_conv_dgrad_bf16": 1,
     "selavi_conv_halo_pack_weights": 1, "selavi_conv_halo_fwd": 1, "selavi_conv_halo_dgrad": 1, "selavi_clip_augment": 1,
 }

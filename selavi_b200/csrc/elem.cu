@@ -279,7 +279,8 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* 
                                     const float4* __restrict__ shift, const float4* __restrict__ mean,
                                     const float4* __restrict__ invstd, const double* __restrict__ sums, double count,
                                     long long total4, int c4n, float4* __restrict__ dz, float4* __restrict__ gres,
-                                    int gres_accumulate, uint2* __restrict__ dz_hi, uint2* __restrict__ dz_lo) {
+                                    int gres_accumulate, uint2* __restrict__ dz_hi, uint2* __restrict__ dz_lo,
+                                    uint2* __restrict__ a_hi, uint2* __restrict__ a_lo) {
     // dz = A*g + B*z + C per channel, A = scale, B = -scale*invstd*m2, C = -scale*m1 - B*mean (m1, m2 = sums / count);
     // the coefficient table lives in shared memory, the element loop is a flat grid-stride stream (HBM-bound)
     extern __shared__ float4 s_coef[];   // [3][c4n]: A | B | C   (+ [c4n] shift for mask_mode 2)
@@ -324,6 +325,15 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ g, const float4* 
             const __nv_bfloat162 l1 = __floats2bfloat162_rn(o.z - __low2float(h1), o.w - __high2float(h1));
             dz_hi[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
             dz_lo[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        }
+        if (a_hi) {   // bf16 hi/lo planes of this unit's OUTPUT ACTIVATION (mode 1: act; mode 2: relu(z*scale+shift)): the input
+                      // operand of the weight gradient of the convolution that consumed it (saves that kernel's split pass)
+            const float4 y = (mask_mode == 2) ? relu4(a) : a;
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(y.x, y.y), h1 = __floats2bfloat162_rn(y.z, y.w);
+            const __nv_bfloat162 l0 = __floats2bfloat162_rn(y.x - __low2float(h0), y.y - __high2float(h0));
+            const __nv_bfloat162 l1 = __floats2bfloat162_rn(y.z - __low2float(h1), y.w - __high2float(h1));
+            a_hi[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+            a_lo[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
         }
         if (gres) {
             float4 rr = gg;
@@ -616,10 +626,11 @@ extern "C" int selavi_bn_bwd_reduce(const float* g, const float* z, const float*
 extern "C" int selavi_bn_bwd_apply(const float* g, const float* z, const float* act, int mask_mode, const float* scale,
                                    const float* shift, const float* mean, const float* invstd, const double* sums,
                                    double count, long long M, int cs, float* dz, float* gres, int gres_accumulate,
-                                   void* dz_hi, void* dz_lo, void* stream) {
+                                   void* dz_hi, void* dz_lo, void* act_hi, void* act_lo, void* stream) {
     if (!g || !z || !scale || !mean || !invstd || !sums || (!dz && !dz_hi) || (cs & 3) || M <= 0 || count <= 0 ||
-        ((dz_hi == nullptr) != (dz_lo == nullptr)))
+        ((dz_hi == nullptr) != (dz_lo == nullptr)) || ((act_hi == nullptr) != (act_lo == nullptr)))
         return selavi_fail(-1, "bn_bwd_apply: bad arguments");
+    if (act_hi && mask_mode == 0) return selavi_fail(-1, "bn_bwd_apply: activation planes need mask_mode 1 or 2");
     if (mask_mode == 1 && !act) return selavi_fail(-1, "bn_bwd_apply: mask_mode 1 needs act");
     if (mask_mode == 2 && !shift) return selavi_fail(-1, "bn_bwd_apply: mask_mode 2 needs shift");
     const int c4n = cs / 4;
@@ -627,7 +638,7 @@ extern "C" int selavi_bn_bwd_apply(const float* g, const float* z, const float* 
     bn_bwd_apply_kernel<<<ew_blocks(total4), EW_THREADS, (size_t)4 * c4n * sizeof(float4), (cudaStream_t)stream>>>(
         (const float4*)g, (const float4*)z, (const float4*)act, mask_mode, (const float4*)scale, (const float4*)shift,
         (const float4*)mean, (const float4*)invstd, sums, count, total4, c4n, (float4*)dz, (float4*)gres, gres_accumulate,
-        (uint2*)dz_hi, (uint2*)dz_lo);
+        (uint2*)dz_hi, (uint2*)dz_lo, (uint2*)act_hi, (uint2*)act_lo);
     LAUNCH_CHECK("bn_bwd_apply");
     return 0;
 }

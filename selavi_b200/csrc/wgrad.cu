@@ -803,7 +803,7 @@ int blocks_for(long long n) {
 // Common driver.  z_hi/z_lo: pre-split bf16 dz (bf16 path) or null; dz: fp32 dz (tf32 path, or bf16 path without pre-split).
 int wgrad_run(const float* src, const float* dz, const void* z_hi_in, const void* z_lo_in, float* dW, const int* geom,
               int ci_real, const float* pro_scale, const float* pro_shift, int pro_relu, void* workspace, int accumulate,
-              int passes, cudaStream_t stream) {
+              int passes, cudaStream_t stream, const void* a_hi_in = nullptr, const void* a_lo_in = nullptr) {
     WgradParams p;
     p.src = src;
     p.dz = dz;
@@ -852,11 +852,16 @@ int wgrad_run(const float* src, const float* dz, const void* z_hi_in, const void
         unsigned char* w = reinterpret_cast<unsigned char*>(workspace) + partial_bytes;
         const size_t a_bytes = align256((size_t)Min * p.cs * 2), z_bytes = align256((size_t)M * p.cd * 2);
         WgradBf16Params q;
-        q.a_hi = reinterpret_cast<const __nv_bfloat16*>(w);
-        q.a_lo = reinterpret_cast<const __nv_bfloat16*>(w + a_bytes);
         const long long a4 = Min * (p.cs / 4), z4 = M * (p.cd / 4);
-        split_bf16_kernel<<<blocks_for(a4), 256, 0, stream>>>((const float4*)src, (const float4*)pro_scale, (const float4*)pro_shift,
-                                                              pro_relu, (uint2*)q.a_hi, (uint2*)q.a_lo, a4, p.cs / 4);
+        if (a_hi_in) {   // the conv input arrives as bf16 hi/lo planes (emitted by selavi_bn_bwd_apply): no split pass
+            q.a_hi = reinterpret_cast<const __nv_bfloat16*>(a_hi_in);
+            q.a_lo = reinterpret_cast<const __nv_bfloat16*>(a_lo_in);
+        } else {
+            q.a_hi = reinterpret_cast<const __nv_bfloat16*>(w);
+            q.a_lo = reinterpret_cast<const __nv_bfloat16*>(w + a_bytes);
+            split_bf16_kernel<<<blocks_for(a4), 256, 0, stream>>>((const float4*)src, (const float4*)pro_scale, (const float4*)pro_shift,
+                                                                  pro_relu, (uint2*)q.a_hi, (uint2*)q.a_lo, a4, p.cs / 4);
+        }
         if (z_hi_in) {
             q.z_hi = reinterpret_cast<const __nv_bfloat16*>(z_hi_in);
             q.z_lo = reinterpret_cast<const __nv_bfloat16*>(z_lo_in);
@@ -936,6 +941,16 @@ extern "C" int selavi_conv_wgrad_bf16(const float* src, const void* z_hi, const 
     if (passes != 1 && passes != 3) return selavi_fail(-1, "conv_wgrad_bf16: passes must be 1 or 3");
     return wgrad_run(src, nullptr, z_hi, z_lo, dW, geom, ci_real, pro_scale, pro_shift, pro_relu, workspace, accumulate, passes,
                      (cudaStream_t)stream);
+}
+
+// same, with BOTH operands already split: a_hi/a_lo = bf16 planes of the conv input activation [pixels_in, cs] (emitted by
+// selavi_bn_bwd_apply of the unit that produced it), z_hi/z_lo = planes of the gradient wrt the conv output
+extern "C" int selavi_conv_wgrad_bf16_planes(const void* a_hi, const void* a_lo, const void* z_hi, const void* z_lo, float* dW,
+                                             const int* geom, int ci_real, void* workspace, int accumulate, int passes, void* stream) {
+    if (!a_hi || !a_lo || !z_hi || !z_lo || !dW || !geom || !workspace) return selavi_fail(-1, "conv_wgrad_bf16_planes: null argument");
+    if (passes != 1 && passes != 3) return selavi_fail(-1, "conv_wgrad_bf16_planes: passes must be 1 or 3");
+    return wgrad_run(nullptr, nullptr, z_hi, z_lo, dW, geom, ci_real, nullptr, nullptr, 0, workspace, accumulate, passes,
+                     (cudaStream_t)stream, a_hi, a_lo);
 }
 
 // x [M, cs] fp32 -> bf16 hi/lo planes, optional fused affine (+ReLU):  hi = bf16(y), lo = bf16(y - hi), y = act(x*scale+shift)

@@ -27,6 +27,10 @@ BWD = os.environ.get("SELAVI_BWD", "bf16x3")
 # forward of the convolutions the tap-reuse kernel does not cover (strided, 7x7, 1x1): "fp16x3" (default; fp16 hi/lo operands
 # like conv_halo.cu, half the stages / shared-memory bytes / MMAs of tf32x3) or "tf32x3"
 IGEMM_FWD = os.environ.get("SELAVI_IGEMM_FWD", "fp16x3")
+# the bf16 hi/lo planes of a convolution's INPUT (operand of its weight gradient) are written by the BatchNorm-backward
+# apply pass of the unit that produced that activation (it reads z anyway) instead of by a separate split pass that reads
+# the fp32 tensor once more; the weight gradient is launched when they exist (one layer later in backward order)
+PLANES_FROM_BN = os.environ.get("SELAVI_PLANES_FROM_BN", "1") == "1"
 
 
 def _stream():
@@ -120,11 +124,15 @@ def _allreduce(t, bn):
 
 
 class Act:
-    """An activation: a materialised tensor, or a raw conv output with a pending per-channel affine (+ReLU)."""
-    __slots__ = ("t", "scale", "shift", "relu", "c")
+    """An activation: a materialised tensor, or a raw conv output with a pending per-channel affine (+ReLU).
+    `key`: data pointer of the tensor through which the BatchNorm-backward pass of the PRODUCING unit will see this
+    activation (its own z for a pending activation / the stem output, the materialised block output otherwise); None for
+    tensors no BatchNorm unit produces (network input, max-pool output).  Weight gradients whose input has a key are
+    deferred until that pass has emitted the activation's bf16 hi/lo planes (PLANES_FROM_BN)."""
+    __slots__ = ("t", "scale", "shift", "relu", "c", "key")
 
-    def __init__(self, t, c, scale=None, shift=None, relu=False):
-        self.t, self.c, self.scale, self.shift, self.relu = t, c, scale, shift, relu
+    def __init__(self, t, c, scale=None, shift=None, relu=False, key=None):
+        self.t, self.c, self.scale, self.shift, self.relu, self.key = t, c, scale, shift, relu, key
 
 
 class ConvRec:
@@ -250,7 +258,7 @@ class TowerRunner:
         for i, (conv, bn) in enumerate(main):
             z, scale, shift, rec, geom = self.conv_bn(act, conv, bn, training, tape)
             recs.append(rec)
-            act = Act(z, geom.co, scale, shift, relu=True)
+            act = Act(z, geom.co, scale, shift, relu=True, key=z.data_ptr())
         rd = None
         if downsample is not None:
             zd, sd, bd, rd, _ = self.conv_bn(x_act, downsample[0], downsample[1], training, tape)
@@ -259,7 +267,7 @@ class TowerRunner:
             y = self.bn_apply(z, scale, shift, res=x_act.t, relu=True)
         if tape is not None:
             tape.append(("block", recs, rd, x_act, y))
-        return Act(y, act.c)
+        return Act(y, act.c, key=y.data_ptr())
 
     def forward(self, net, x, training, tape):
         lib = _lib.lib()
@@ -279,11 +287,11 @@ class TowerRunner:
         if self.kind == "video":
             stem = net.stem
             z0, s0, b0, r0, g0 = self.conv_bn(act, stem[0], stem[1], training, tape)
-            z1, s1, b1, r1, g1 = self.conv_bn(Act(z0, g0.co, s0, b0, True), stem[3], stem[4], training, tape)
+            z1, s1, b1, r1, g1 = self.conv_bn(Act(z0, g0.co, s0, b0, True, key=z0.data_ptr()), stem[3], stem[4], training, tape)
             a = self.bn_apply(z1, s1, b1, relu=True)
             if tape is not None:
                 tape.append(("vstem", r0, r1))
-            act = Act(a, g1.co)
+            act = Act(a, g1.co, key=z1.data_ptr())     # a == relu(bn(z1)): the stem unit r1 re-creates it in backward
             for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
                 for blk in layer:
                     main = [(blk.conv1[0][0], blk.conv1[0][1]), (blk.conv1[0][3], blk.conv1[1]),
@@ -345,29 +353,25 @@ class TowerRunner:
             z_lo = torch.empty(z.shape, dtype=torch.bfloat16, device=dev)
         else:
             dz = torch.empty_like(z)
+        # weight gradients of the convolutions that consumed THIS unit's activation are waiting for its bf16 planes
+        my_key = (act_mask.data_ptr() if mask_mode == 1 else z.data_ptr()) if mask_mode in (1, 2) else None
+        waiting = self._pending.pop(my_key, None) if my_key is not None else None
+        a_hi = a_lo = None
+        if waiting:
+            a_hi = torch.empty(z.shape, dtype=torch.bfloat16, device=dev)
+            a_lo = torch.empty(z.shape, dtype=torch.bfloat16, device=dev)
         _lib.check(lib.selavi_bn_bwd_apply(_lib.ptr(g), _lib.ptr(z), _lib.ptr(act_mask), mask_mode, _lib.ptr(rec.scale),
                                            _lib.ptr(rec.shift), _lib.ptr(rec.mean), _lib.ptr(rec.invstd), _lib.ptr(sums),
                                            rec.count, M, cs, _lib.ptr(dz), _lib.ptr(gres), 1 if gres_accumulate else 0,
-                                           _lib.ptr(z_hi), _lib.ptr(z_lo), _stream()), "selavi_bn_bwd_apply")
+                                           _lib.ptr(z_hi), _lib.ptr(z_lo), _lib.ptr(a_hi), _lib.ptr(a_lo), _stream()), "selavi_bn_bwd_apply")
+        for job in waiting or ():
+            self._launch_wgrad(job, grads, a_hi, a_lo)
         if need_dw:
-            dw = torch.empty_like(conv.weight)
-            if bf16 and WGRAD_STREAM:
-                main, side = torch.cuda.current_stream(dev), _side_stream(dev)
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    ops.conv_wgrad_bf16(inp.t, z_hi, z_lo, geom, dw, scale=inp.scale, shift=inp.shift, relu=inp.relu,
-                                        passes=3 if PASSES == 3 else 1)
-                for t in (inp.t, z_hi, z_lo, dw, inp.scale, inp.shift):
-                    if t is not None:
-                        t.record_stream(side)
-                self._side_busy = True
-            elif bf16:
-                ops.conv_wgrad_bf16(inp.t, z_hi, z_lo, geom, dw, scale=inp.scale, shift=inp.shift, relu=inp.relu,
-                                    passes=3 if PASSES == 3 else 1)
+            job = (conv, geom, inp, z_hi, z_lo, dz)
+            if bf16 and PLANES_FROM_BN and inp.key is not None:
+                self._pending.setdefault(inp.key, []).append(job)
             else:
-                ops.conv_wgrad(inp.t, dz, geom, dw, scale=inp.scale, shift=inp.shift, relu=inp.relu,
-                               passes=13 if PASSES == 3 else 11)
-            grads[conv.weight] = dw
+                self._launch_wgrad(job, grads, None, None)
         if not want_dx:
             return None
         if bf16:
@@ -380,12 +384,46 @@ class TowerRunner:
         wpt = _packed(conv, geom, 1)
         return ops.conv_dgrad(dz, wpt, geom, out=dx_out, accumulate=dx_accumulate, passes=PASSES)
 
+    def _launch_wgrad(self, job, grads, a_hi, a_lo):
+        """Weight gradient of one convolution, on the side stream paired with the current stream.  a_hi/a_lo: bf16 planes
+        of the conv input (from the producing unit's BatchNorm-backward pass) or None (split inside the call)."""
+        conv, geom, inp, z_hi, z_lo, dz = job
+        dev = conv.weight.device
+        dw = torch.empty_like(conv.weight)
+        passes = 3 if PASSES == 3 else 1
+
+        def run():
+            if a_hi is not None:
+                ops.conv_wgrad_bf16_planes(a_hi, a_lo, z_hi, z_lo, geom, dw, passes=passes)
+            else:
+                ops.conv_wgrad_bf16(inp.t, z_hi, z_lo, geom, dw, scale=inp.scale, shift=inp.shift, relu=inp.relu, passes=passes)
+
+        if z_hi is None:     # SELAVI_BWD=tf32x3
+            ops.conv_wgrad(inp.t, dz, geom, dw, scale=inp.scale, shift=inp.shift, relu=inp.relu, passes=13 if PASSES == 3 else 11)
+        elif WGRAD_STREAM:
+            main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                run()
+            for t in (inp.t, z_hi, z_lo, dw, inp.scale, inp.shift, a_hi, a_lo):
+                if t is not None:
+                    t.record_stream(side)
+            self._side_busy = True
+        else:
+            run()
+        grads[conv.weight] = dw
+
     def backward(self, tape, dfeat, grads):
         self._side_busy = False
         self._comm_busy = False
         self._reduced = set()
+        self._pending = {}
         try:
             self._backward(tape, dfeat, grads)
+            for jobs in list(self._pending.values()):      # (no producing unit came by: cannot happen for these towers)
+                for job in jobs:
+                    self._launch_wgrad(job, grads, None, None)
+            self._pending = {}
             self._reduce_ready(grads, dfeat.device, final=True)
         finally:
             main = torch.cuda.current_stream(dfeat.device)

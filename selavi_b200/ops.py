@@ -330,6 +330,29 @@ def conv_dgrad_bf16(z_hi, z_lo, wpack_bf16, geom, out=None, accumulate=False, pa
     return out
 
 
+def conv_wgrad_bf16_planes(a_hi, a_lo, z_hi, z_lo, geom, dw, accumulate=False, passes=3):
+    """weight gradient with BOTH operands pre-split: a_hi/a_lo = bf16 planes of the conv input activation (emitted by the
+    BatchNorm-backward apply pass of the unit that produced it), z_hi/z_lo = planes of the gradient wrt the conv output"""
+    _chk_bf16(a_hi, geom.in_shape(), "a_hi")
+    _chk_bf16(a_lo, geom.in_shape(), "a_lo")
+    _chk_bf16(z_hi, geom.out_shape(), "z_hi")
+    _chk_bf16(z_lo, geom.out_shape(), "z_lo")
+    if not (dw.is_cuda and dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == geom.co * geom.ci * geom.taps):
+        raise ValueError("dw must be a contiguous fp32 CUDA tensor in the torch weight layout")
+    lib = _lib.lib()
+    nbytes = lib.selavi_wgrad_workspace_bytes(geom.arr(0))
+    key = (a_hi.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _wgrad_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=a_hi.device)
+        _wgrad_ws[key] = ws
+    with _Guard(a_hi.device), _Prof("conv_wgrad", geom, "wgrad_bf16_kernel(+reduce)"):
+        _lib.check(lib.selavi_conv_wgrad_bf16_planes(_lib.ptr(a_hi), _lib.ptr(a_lo), _lib.ptr(z_hi), _lib.ptr(z_lo), _lib.ptr(dw),
+                                                     geom.arr(0), geom.ci, _lib.ptr(ws), 1 if accumulate else 0, passes,
+                                                     _lib.stream_ptr()), "selavi_conv_wgrad_bf16_planes")
+    return dw
+
+
 def conv_wgrad_bf16(x, z_hi, z_lo, geom, dw, scale=None, shift=None, relu=False, accumulate=False, passes=3):
     _chk(x, geom.in_shape(), "x")
     _chk_bf16(z_hi, geom.out_shape(), "z_hi")
