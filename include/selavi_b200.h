@@ -136,6 +136,14 @@ int selavi_conv_halo_fwd(const float* src, float* dst, const void* wpack, const 
  * selavi_conv_halo_pack_weights with the mode-1 geometry (k_real = co; forward: k_real = ci). */
 int selavi_conv_halo_dgrad(const void* z_hi, const void* z_lo, float* dx, const void* wpack, const int* geom,
                            int accumulate, int flags, void* stream);
+/* same, and the epilogue also emits the per-tile partial sums of the BatchNorm-backward pass that consumes dx:
+ * stats_partial [m_tiles][2][ntiles*bnt] (tile counts of selavi_conv_halo_plan in mode 1) = (sum g*m, sum g*m*zhat), g = dx,
+ * m = (bn_z*bn_scale+bn_shift > 0), zhat = (bn_z-bn_mean)*bn_invstd, for the unit whose raw output is bn_z [pixels_in, cis].
+ * selavi_bn_reduce_partials turns them into the sums selavi_bn_bwd_reduce (mask_mode 2) would produce, without reading
+ * dx and bn_z again from HBM.  The gradient is written (not accumulated). */
+int selavi_conv_halo_dgrad_bnstats(const void* z_hi, const void* z_lo, float* dx, const void* wpack, const int* geom,
+                                   const float* bn_z, const float* bn_scale, const float* bn_shift, const float* bn_mean,
+                                   const float* bn_invstd, float* stats_partial, int flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm (train mode, nn.BatchNorm{1,2,3}d / SyncBatchNorm semantics), residual add, ReLU, pooling, layout,

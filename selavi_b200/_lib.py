@@ -66,6 +66,8 @@ SIGNATURES = {
     "selavi_conv_halo_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                      c_void_p]),
     "selavi_conv_halo_dgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "selavi_conv_halo_dgrad_bnstats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "selavi_relu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "selavi_maxpool3x3s2_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "selavi_maxpool3x3s2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
@@ -120,7 +122,7 @@ KERNELS_PER_CALL = {
     "selavi_heads_bn_bwd_apply": 1, "selavi_heads_sum_masked": 1, "selavi_heads_colsum": 1, "selavi_ce_loss": 2,
     "selavi_mel_logfbank": 1, "selavi_split_bf16": 1, "selavi_p2p_allreduce_f64": 1, "selavi_conv_wgrad_bf16": 3, "selavi_conv_wgrad_bf16_planes": 2,
     "selavi_dgrad_pack_weights": 1, "selavi_conv_dgrad_bf16": 1,
-    "selavi_conv_halo_pack_weights": 1, "selavi_conv_halo_fwd": 1, "selavi_conv_halo_dgrad": 1, "selavi_clip_augment": 1,
+    "selavi_conv_halo_pack_weights": 1, "selavi_conv_halo_fwd": 1, "selavi_conv_halo_dgrad": 1, "selavi_conv_halo_dgrad_bnstats": 1, "selavi_clip_augment": 1,
 }
 COUNT_CALLS = False
 CALLS = {}

@@ -48,6 +48,8 @@ struct HaloParams {
     const float* pro_scale;      // [cs] or null
     const float* pro_shift;
     float* stats;                // [m_tiles][2][ntiles*bnt] or null
+    sv::EpiBwdStat bwd;          // data gradient: the following BatchNorm-backward statistics instead of sum / sum of squares
+    int has_bwd;
     int mode;                    // 0 temporal 3x1x1, 1 spatial 1x3x3
     int nb, T, H, W, cs, cd;
     int S, WP;
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(HL_THREADS, 1) conv_halo_kernel(const HaloPara
             sv::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * (p.tmem_cols >> 1);
             sv::epi_drain_tile(taddr, p.bnt, p.oscale, row_ok, stg, row_pix, p.dst, p.cd, n_base, p.accumulate,
-                               valid && !(p.dbg & 8), p.stats != nullptr ? my_stat : nullptr, lane);
+                               valid && !(p.dbg & 8), p.stats != nullptr ? my_stat : nullptr, lane, p.has_bwd ? &p.bwd : nullptr);
             sv::tc_fence_before();
             __syncwarp();
             if (lane == 0) arrive_leader(&tempty_bar[acc]);
@@ -765,11 +767,34 @@ extern "C" int selavi_conv_halo_fwd(const float* src, float* dst, const void* wp
     p.pro_scale = pro_scale; p.pro_shift = pro_shift; p.stats = stats_partial;
     p.pro_relu = pro_relu;
     p.src_kind = 0; p.accumulate = 0; p.oscale = HL_OSCALE;
+    p.has_bwd = 0;
+    p.bwd = sv::EpiBwdStat{nullptr, nullptr, nullptr, nullptr, nullptr};
     return hl_launch(pl, p, flags, stream);
 }
 
+static int hl_dgrad(const void* z_hi, const void* z_lo, float* dx, const void* wpack, const int* geom, int accumulate,
+                    const sv::EpiBwdStat* bwd, float* stats_partial, int flags, void* stream);
+
 extern "C" int selavi_conv_halo_dgrad(const void* z_hi, const void* z_lo, float* dx, const void* wpack, const int* geom,
                                       int accumulate, int flags, void* stream) {
+    return hl_dgrad(z_hi, z_lo, dx, wpack, geom, accumulate, nullptr, nullptr, flags, stream);
+}
+
+// Same, and the epilogue also emits the per-tile partial sums of the BatchNorm-backward pass of the unit that produced the
+// activation dx is the gradient of: stats_partial [m_tiles][2][ntiles*bnt] = (sum g*m, sum g*m*zhat) with g = dx,
+// m = (bn_z*bn_scale+bn_shift > 0), zhat = (bn_z-bn_mean)*bn_invstd; bn_z [pixels_in, cis] fp32, the vectors [cis].
+// Reduce with selavi_bn_reduce_partials; replaces selavi_bn_bwd_reduce (mask_mode 2) for that unit.  accumulate must be 0.
+extern "C" int selavi_conv_halo_dgrad_bnstats(const void* z_hi, const void* z_lo, float* dx, const void* wpack, const int* geom,
+                                              const float* bn_z, const float* bn_scale, const float* bn_shift,
+                                              const float* bn_mean, const float* bn_invstd, float* stats_partial, int flags,
+                                              void* stream) {
+    if (!bn_z || !bn_scale || !bn_shift || !bn_mean || !bn_invstd || !stats_partial) return selavi_fail(-1, "conv_halo_dgrad_bnstats: null argument");
+    const sv::EpiBwdStat bwd{bn_z, bn_scale, bn_shift, bn_mean, bn_invstd};
+    return hl_dgrad(z_hi, z_lo, dx, wpack, geom, 0, &bwd, stats_partial, flags, stream);
+}
+
+static int hl_dgrad(const void* z_hi, const void* z_lo, float* dx, const void* wpack, const int* geom, int accumulate,
+                    const sv::EpiBwdStat* bwd, float* stats_partial, int flags, void* stream) {
     if (!z_hi || !z_lo || !dx || !wpack || !geom) return selavi_fail(-1, "conv_halo_dgrad: null argument");
     if (geom[0] != 1) return selavi_fail(-1, "conv_halo_dgrad: geometry must be in dgrad mode");
     HaloPlan pl;
@@ -779,9 +804,11 @@ extern "C" int selavi_conv_halo_dgrad(const void* z_hi, const void* z_lo, float*
     p.src_hi = reinterpret_cast<const __nv_bfloat16*>(z_hi);
     p.src_lo = reinterpret_cast<const __nv_bfloat16*>(z_lo);
     p.dst = dx; p.wpack = reinterpret_cast<const unsigned char*>(wpack);
-    p.pro_scale = nullptr; p.pro_shift = nullptr; p.stats = nullptr;
+    p.pro_scale = nullptr; p.pro_shift = nullptr; p.stats = stats_partial;
     p.pro_relu = 0;
     p.src_kind = 1; p.accumulate = accumulate ? 1 : 0; p.oscale = 1.f;
+    p.has_bwd = bwd != nullptr ? 1 : 0;
+    p.bwd = bwd ? *bwd : sv::EpiBwdStat{nullptr, nullptr, nullptr, nullptr, nullptr};
     return hl_launch(pl, p, flags, stream);
 }
 

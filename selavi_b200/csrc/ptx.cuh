@@ -321,16 +321,40 @@ __device__ __forceinline__ float ld_shared_f1(uint32_t addr) {
 //             (global row index of each TMEM lane, -1 = no such row), written by the caller + __syncwarp()
 //   col0    : destination column of the first accumulator column; columns >= cd are not stored
 //   stat    : this warp's [2][256] sum scratch, already offset to the group's first column; nullptr = no statistics
-template <int GW>
-__device__ __forceinline__ void epi_drain_group(uint32_t taddr, float oscale, bool row_ok, uint32_t stg, const int* row_pix,
-                                                float* __restrict__ dst, int cd, int col0, int accumulate, bool do_store,
-                                                float* stat, int lane);
+// Statistics of the BatchNorm-BACKWARD pass that follows a data-gradient kernel, fused into its epilogue: the gradient g
+// this kernel writes is the upstream gradient of the unit whose raw output is `z` (activation relu(z*scale+shift)), and
+// that unit's backward needs sum(g*m) and sum(g*m*zhat) per channel (m = ReLU mask, zhat = (z-mean)*invstd).  Computing
+// them here, where g sits in registers, saves the separate reduce pass that reads g and z again from HBM.
+struct EpiBwdStat {
+    const float* z;        // [pixels][cd]
+    const float* scale;    // [cd] each
+    const float* shift;
+    const float* mean;
+    const float* invstd;
+};
 
 template <int GW>
 __device__ __forceinline__ void epi_drain_group(uint32_t taddr, float oscale, bool row_ok, uint32_t stg, const int* row_pix,
                                                 float* __restrict__ dst, int cd, int col0, int accumulate, bool do_store,
-                                                float* stat, int lane) {
+                                                float* stat, int lane, const EpiBwdStat* bwd = nullptr) {
     static_assert(GW == 32 || GW == 16, "group width");
+    constexpr int CPR = GW / 4;      // 16-byte chunks per row segment
+    constexpr int RPI = 32 / CPR;    // row segments per store instruction
+    const int j = lane % CPR, rsub = lane / CPR;
+    const int col = col0 + j * 4;
+    const bool want_bwd = bwd != nullptr && stat != nullptr;
+    // fused BatchNorm-backward statistics: this lane's z values are requested FIRST, so that their HBM / L2 latency is
+    // hidden behind the TMEM drain and the staging pass (issued inside the store loop they serialise behind the stores:
+    // measured 2x on the whole data-gradient kernel)
+    float4 zz[CPR];
+    if (want_bwd) {
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+            const int pix = row_pix[i * RPI + rsub];
+            zz[i] = (pix >= 0 && col < cd) ? __ldg(reinterpret_cast<const float4*>(bwd->z + (size_t)pix * cd + col))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
     uint32_t av[GW];
     if constexpr (GW == 32) tmem_ld32(taddr, av);
     else tmem_ld16(taddr, av);
@@ -344,7 +368,7 @@ __device__ __forceinline__ void epi_drain_group(uint32_t taddr, float oscale, bo
         st_shared_f4(my_row + (uint32_t)((j ^ (lane & 7)) << 4), f[0], f[1], f[2], f[3]);
     }
     __syncwarp();
-    if (stat != nullptr && lane < GW) {
+    if (stat != nullptr && bwd == nullptr && lane < GW) {
         float s1 = 0.f, s2 = 0.f;
         const uint32_t word = (uint32_t)(lane & 3) * 4u;
         const int ch = lane >> 2;
@@ -357,25 +381,54 @@ __device__ __forceinline__ void epi_drain_group(uint32_t taddr, float oscale, bo
         stat[lane] = s1;
         stat[256 + lane] = s2;
     }
-    constexpr int CPR = GW / 4;      // 16-byte chunks per row segment
-    constexpr int RPI = 32 / CPR;    // row segments per store instruction
-    const int j = lane % CPR, rsub = lane / CPR;
-    const int col = col0 + j * 4;
+    float4 b_sc = make_float4(0.f, 0.f, 0.f, 0.f), b_sh = b_sc, b_mu = b_sc, b_is = b_sc;
+    float4 t1 = b_sc, t2 = b_sc;     // sum g*m, sum g*m*zhat of this lane's 4 columns over its rows
+    if (want_bwd && col < cd) {
+        b_sc = __ldg(reinterpret_cast<const float4*>(bwd->scale + col));
+        b_sh = __ldg(reinterpret_cast<const float4*>(bwd->shift + col));
+        b_mu = __ldg(reinterpret_cast<const float4*>(bwd->mean + col));
+        b_is = __ldg(reinterpret_cast<const float4*>(bwd->invstd + col));
+    }
 #pragma unroll
     for (int i = 0; i < CPR; ++i) {   // 32 / RPI == CPR iterations
         const int rr = i * RPI + rsub;
         const int pix = row_pix[rr];
         float4 v = ld_shared_f4(stg + (uint32_t)rr * 128u + (uint32_t)((j ^ (rr & 7)) << 4));
-        if (do_store && pix >= 0 && col < cd) {
-            float4* dp = reinterpret_cast<float4*>(dst + (size_t)pix * cd + col);
-            if (accumulate) {
-                const float4 old = *dp;
-                v.x += old.x;
-                v.y += old.y;
-                v.z += old.z;
-                v.w += old.w;
+        if (pix >= 0 && col < cd) {
+            if (want_bwd) {
+                const float4 q = zz[i];
+                const float gx = fmaf(q.x, b_sc.x, b_sh.x) > 0.f ? v.x : 0.f, gy = fmaf(q.y, b_sc.y, b_sh.y) > 0.f ? v.y : 0.f;
+                const float gz = fmaf(q.z, b_sc.z, b_sh.z) > 0.f ? v.z : 0.f, gw = fmaf(q.w, b_sc.w, b_sh.w) > 0.f ? v.w : 0.f;
+                t1.x += gx; t1.y += gy; t1.z += gz; t1.w += gw;
+                t2.x = fmaf(gx, (q.x - b_mu.x) * b_is.x, t2.x);
+                t2.y = fmaf(gy, (q.y - b_mu.y) * b_is.y, t2.y);
+                t2.z = fmaf(gz, (q.z - b_mu.z) * b_is.z, t2.z);
+                t2.w = fmaf(gw, (q.w - b_mu.w) * b_is.w, t2.w);
             }
-            *dp = v;
+            if (do_store) {
+                float4* dp = reinterpret_cast<float4*>(dst + (size_t)pix * cd + col);
+                if (accumulate) {
+                    const float4 old = *dp;
+                    v.x += old.x;
+                    v.y += old.y;
+                    v.z += old.z;
+                    v.w += old.w;
+                }
+                *dp = v;
+            }
+        }
+    }
+    if (want_bwd) {   // lanes j, j+CPR, j+2*CPR, ... hold the same columns: fold them (fixed order), lane j publishes
+#pragma unroll
+        for (int o = CPR; o < 32; o <<= 1) {
+            t1.x += __shfl_xor_sync(0xffffffffu, t1.x, o); t1.y += __shfl_xor_sync(0xffffffffu, t1.y, o);
+            t1.z += __shfl_xor_sync(0xffffffffu, t1.z, o); t1.w += __shfl_xor_sync(0xffffffffu, t1.w, o);
+            t2.x += __shfl_xor_sync(0xffffffffu, t2.x, o); t2.y += __shfl_xor_sync(0xffffffffu, t2.y, o);
+            t2.z += __shfl_xor_sync(0xffffffffu, t2.z, o); t2.w += __shfl_xor_sync(0xffffffffu, t2.w, o);
+        }
+        if (lane < CPR) {
+            stat[j * 4 + 0] = t1.x; stat[j * 4 + 1] = t1.y; stat[j * 4 + 2] = t1.z; stat[j * 4 + 3] = t1.w;
+            stat[256 + j * 4 + 0] = t2.x; stat[256 + j * 4 + 1] = t2.y; stat[256 + j * 4 + 2] = t2.z; stat[256 + j * 4 + 3] = t2.w;
         }
     }
     __syncwarp();
@@ -384,14 +437,14 @@ __device__ __forceinline__ void epi_drain_group(uint32_t taddr, float oscale, bo
 // all bnt (multiple of 16) columns of one accumulator; stat = this warp's [2][256] scratch or nullptr
 __device__ __forceinline__ void epi_drain_tile(uint32_t taddr, int bnt, float oscale, bool row_ok, uint32_t stg, const int* row_pix,
                                                float* __restrict__ dst, int cd, int n_base, int accumulate, bool do_store,
-                                               float* stat, int lane) {
+                                               float* stat, int lane, const EpiBwdStat* bwd = nullptr) {
     int c0 = 0;
     for (; c0 + 32 <= bnt; c0 += 32)
         epi_drain_group<32>(taddr + (uint32_t)c0, oscale, row_ok, stg, row_pix, dst, cd, n_base + c0, accumulate, do_store,
-                            stat ? stat + c0 : nullptr, lane);
+                            stat ? stat + c0 : nullptr, lane, bwd);
     if (c0 < bnt)
         epi_drain_group<16>(taddr + (uint32_t)c0, oscale, row_ok, stg, row_pix, dst, cd, n_base + c0, accumulate, do_store,
-                            stat ? stat + c0 : nullptr, lane);
+                            stat ? stat + c0 : nullptr, lane, bwd);
 }
 
 }  // namespace sv

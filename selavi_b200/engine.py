@@ -31,6 +31,10 @@ IGEMM_FWD = os.environ.get("SELAVI_IGEMM_FWD", "fp16x3")
 # apply pass of the unit that produced that activation (it reads z anyway) instead of by a separate split pass that reads
 # the fp32 tensor once more; the weight gradient is launched when they exist (one layer later in backward order)
 PLANES_FROM_BN = os.environ.get("SELAVI_PLANES_FROM_BN", "1") == "1"
+# the per-channel sums of a unit's BatchNorm-backward pass (sum g*mask, sum g*mask*zhat) are accumulated in the epilogue
+# of the tap-reuse data-gradient kernel that PRODUCES g (it holds g in registers and reads the unit's z tile once) instead
+# of by a separate pass that reads g and z again from HBM
+FUSE_BN_BWD_STATS = os.environ.get("SELAVI_FUSE_BN_BWD_STATS", "1") == "1"
 
 
 def _stream():
@@ -129,15 +133,16 @@ class Act:
     activation (its own z for a pending activation / the stem output, the materialised block output otherwise); None for
     tensors no BatchNorm unit produces (network input, max-pool output).  Weight gradients whose input has a key are
     deferred until that pass has emitted the activation's bf16 hi/lo planes (PLANES_FROM_BN)."""
-    __slots__ = ("t", "scale", "shift", "relu", "c", "key")
+    __slots__ = ("t", "scale", "shift", "relu", "c", "key", "unit")
 
-    def __init__(self, t, c, scale=None, shift=None, relu=False, key=None):
+    def __init__(self, t, c, scale=None, shift=None, relu=False, key=None, unit=None):
         self.t, self.c, self.scale, self.shift, self.relu, self.key = t, c, scale, shift, relu, key
+        self.unit = unit      # ConvRec of the conv+BN unit whose PENDING activation this is (its backward consumes our dgrad)
 
 
 class ConvRec:
     """Everything the backward pass needs about one conv+BN unit."""
-    __slots__ = ("conv", "bn", "geom", "inp", "z", "scale", "shift", "mean", "invstd", "count")
+    __slots__ = ("conv", "bn", "geom", "inp", "z", "scale", "shift", "mean", "invstd", "count", "fused_stats")
 
 
 def _packed_dgrad_bf16(conv, geom):
@@ -231,6 +236,7 @@ class TowerRunner:
                 rec = ConvRec()
                 rec.conv, rec.bn, rec.geom, rec.inp, rec.z = conv, bn, geom, act, z
                 rec.scale, rec.shift, rec.mean, rec.invstd, rec.count = scale, shift, mean, invstd, count
+                rec.fused_stats = None
         else:
             if halo:
                 z = ops.conv_forward_halo(x, wp, geom, scale=act.scale, shift=act.shift, relu=act.relu, stats=None)
@@ -258,7 +264,7 @@ class TowerRunner:
         for i, (conv, bn) in enumerate(main):
             z, scale, shift, rec, geom = self.conv_bn(act, conv, bn, training, tape)
             recs.append(rec)
-            act = Act(z, geom.co, scale, shift, relu=True, key=z.data_ptr())
+            act = Act(z, geom.co, scale, shift, relu=True, key=z.data_ptr(), unit=rec)
         rd = None
         if downsample is not None:
             zd, sd, bd, rd, _ = self.conv_bn(x_act, downsample[0], downsample[1], training, tape)
@@ -287,7 +293,7 @@ class TowerRunner:
         if self.kind == "video":
             stem = net.stem
             z0, s0, b0, r0, g0 = self.conv_bn(act, stem[0], stem[1], training, tape)
-            z1, s1, b1, r1, g1 = self.conv_bn(Act(z0, g0.co, s0, b0, True, key=z0.data_ptr()), stem[3], stem[4], training, tape)
+            z1, s1, b1, r1, g1 = self.conv_bn(Act(z0, g0.co, s0, b0, True, key=z0.data_ptr(), unit=r0), stem[3], stem[4], training, tape)
             a = self.bn_apply(z1, s1, b1, relu=True)
             if tape is not None:
                 tape.append(("vstem", r0, r1))
@@ -330,12 +336,18 @@ class TowerRunner:
         geom, z = rec.geom, rec.z
         dev = z.device
         cs, M = geom.cos, geom.m_out
-        nblk = lib.selavi_bn_bwd_blocks(M)
-        partial = torch.empty(nblk * 2 * cs, dtype=torch.float32, device=dev)
         sums = torch.empty(2 * cs, dtype=torch.float64, device=dev)
-        _lib.check(lib.selavi_bn_bwd_reduce(_lib.ptr(g), _lib.ptr(z), _lib.ptr(act_mask), mask_mode, _lib.ptr(rec.scale),
-                                            _lib.ptr(rec.shift), _lib.ptr(rec.mean), _lib.ptr(rec.invstd), M, cs,
-                                            _lib.ptr(partial), _lib.ptr(sums), _stream()), "selavi_bn_bwd_reduce")
+        fused, rec.fused_stats = rec.fused_stats, None
+        if fused is not None and mask_mode == 2:
+            # the data-gradient kernel that wrote g left the per-tile partial sums of this very reduction
+            _lib.check(lib.selavi_bn_reduce_partials(_lib.ptr(fused), fused.shape[0], fused.shape[2], cs, _lib.ptr(sums),
+                                                     _stream()), "selavi_bn_reduce_partials")
+        else:
+            nblk = lib.selavi_bn_bwd_blocks(M)
+            partial = torch.empty(nblk * 2 * cs, dtype=torch.float32, device=dev)
+            _lib.check(lib.selavi_bn_bwd_reduce(_lib.ptr(g), _lib.ptr(z), _lib.ptr(act_mask), mask_mode, _lib.ptr(rec.scale),
+                                                _lib.ptr(rec.shift), _lib.ptr(rec.mean), _lib.ptr(rec.invstd), M, cs,
+                                                _lib.ptr(partial), _lib.ptr(sums), _stream()), "selavi_bn_bwd_reduce")
         bn = rec.bn
         if bn.weight is not None and bn.weight.requires_grad:
             s32 = sums.view(2, cs)[:, :geom.co].float()
@@ -377,8 +389,17 @@ class TowerRunner:
         if bf16:
             plan = ops.halo_plan(geom, 1) if PASSES == 3 else None
             if plan is not None:
-                return ops.conv_dgrad_halo(z_hi, z_lo, _packed(conv, geom, ("halo_dgrad", plan[1], plan[2])), geom, out=dx_out,
-                                           accumulate=dx_accumulate)
+                wpd = _packed(conv, geom, ("halo_dgrad", plan[1], plan[2]))
+                prev = inp.unit
+                # measured (tools/dgrad_fused_bench.py, profiles/r02_dgrad_fused_stats.txt): pays on the spatial convs (narrow
+                # output, long MMA phase per tile: +0.02 ms against a 0.16 ms reduce pass on layer 1) and LOSES on the temporal
+                # ones (144..1152-wide output, epilogue-bound: +0.47 ms against 0.32 ms), so only kt == 1 is fused
+                if (FUSE_BN_BWD_STATS and geom.kt == 1 and prev is not None and dx_out is None and not dx_accumulate
+                        and prev.z is inp.t):
+                    dx, prev.fused_stats = ops.conv_dgrad_halo(z_hi, z_lo, wpd, geom,
+                                                               bn=(prev.z, prev.scale, prev.shift, prev.mean, prev.invstd))
+                    return dx
+                return ops.conv_dgrad_halo(z_hi, z_lo, wpd, geom, out=dx_out, accumulate=dx_accumulate)
             return ops.conv_dgrad_bf16(z_hi, z_lo, _packed_dgrad_bf16(conv, geom), geom, out=dx_out, accumulate=dx_accumulate,
                                        passes=3 if PASSES == 3 else 1)
         wpt = _packed(conv, geom, 1)

@@ -193,13 +193,28 @@ def pack_weights_halo(w, geom, out=None, mode=0):
     return out
 
 
-def conv_dgrad_halo(z_hi, z_lo, wpack, geom, out=None, accumulate=False):
+def conv_dgrad_halo(z_hi, z_lo, wpack, geom, out=None, accumulate=False, bn=None):
+    """bn = (z, scale, shift, mean, invstd) of the unit that produced the activation whose gradient this is: the epilogue
+    then also emits that unit's BatchNorm-backward partial sums; returns (dx, stats_partial [m_tiles, 2, bnt*ntiles])."""
     _chk_bf16(z_hi, geom.out_shape(), "z_hi")
     _chk_bf16(z_lo, geom.out_shape(), "z_lo")
     if out is None:
         out = torch.empty(geom.in_shape(), dtype=torch.float32, device=z_hi.device)
         accumulate = False
     _chk(out, geom.in_shape(), "dx")
+    if bn is not None:
+        if accumulate:
+            raise ValueError("fused BatchNorm-backward statistics need a written (not accumulated) gradient")
+        bz, bsc, bsh, bmu, bis = bn
+        _chk(bz, geom.in_shape(), "bn z")
+        mt, bnt, nt, _ = halo_plan(geom, 1)
+        stats = torch.empty((mt, 2, bnt * nt), dtype=torch.float32, device=z_hi.device)
+        with _Guard(z_hi.device), _Prof("conv_dgrad", geom, "conv_halo_kernel[dgrad bf16x3]"):
+            _lib.check(_lib.lib().selavi_conv_halo_dgrad_bnstats(_lib.ptr(z_hi), _lib.ptr(z_lo), _lib.ptr(out), _lib.ptr(wpack),
+                                                                 geom.arr(1), _lib.ptr(bz), _lib.ptr(bsc), _lib.ptr(bsh), _lib.ptr(bmu),
+                                                                 _lib.ptr(bis), _lib.ptr(stats), HALO_FLAGS, _lib.stream_ptr()),
+                       "selavi_conv_halo_dgrad_bnstats")
+        return out, stats
     with _Guard(z_hi.device), _Prof("conv_dgrad", geom, "conv_halo_kernel[dgrad bf16x3]"):
         _lib.check(_lib.lib().selavi_conv_halo_dgrad(_lib.ptr(z_hi), _lib.ptr(z_lo), _lib.ptr(out), _lib.ptr(wpack), geom.arr(1),
                                                      1 if accumulate else 0, HALO_FLAGS, _lib.stream_ptr()),

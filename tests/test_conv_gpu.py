@@ -230,6 +230,51 @@ def test_conv_dgrad_halo(cuda_device, name, monkeypatch):
 
 
 @pytest.mark.parametrize("name", sorted(HALO_LAYERS))
+def test_conv_dgrad_halo_fused_bn_backward_stats(cuda_device, name, monkeypatch):
+    """the data-gradient epilogue also emits sum(g*m), sum(g*m*zhat) of the BatchNorm-backward pass that consumes g
+    (m = relu mask of the producing unit, zhat its normalised output): same dx bit for bit, sums vs float64 torch, and
+    the activation planes emitted by bn_bwd_apply equal split_bf16 of the activation"""
+    from selavi_b200 import _lib, ops
+    monkeypatch.setattr(ops, "FWD_KERNEL", "halo")
+    x, w, geom, p = _mk_halo(name, cuda_device)
+    g = torch.Generator(device=cuda_device).manual_seed(11)
+    dz = torch.randn(geom.out_shape(), device=cuda_device, generator=g)
+    dz[..., geom.co:] = 0
+    z_hi, z_lo = ops.split_bf16(dz)
+    wp = ops.pack_weights_halo(w, geom, mode=1)
+    dx_ref = ops.conv_dgrad_halo(z_hi, z_lo, wp, geom)
+    cs = geom.cis
+    zprev = torch.randn(geom.in_shape(), device=cuda_device, generator=g)
+    zprev[..., geom.ci:] = 0
+    scale = torch.rand(cs, device=cuda_device, generator=g) + 0.5
+    shift = torch.randn(cs, device=cuda_device, generator=g) * 0.3
+    mean = torch.randn(cs, device=cuda_device, generator=g) * 0.2
+    invstd = torch.rand(cs, device=cuda_device, generator=g) + 0.5
+    for v in (scale, shift, mean, invstd):
+        v[geom.ci:] = 0
+    dx, stats = ops.conv_dgrad_halo(z_hi, z_lo, wp, geom, bn=(zprev, scale, shift, mean, invstd))
+    assert torch.equal(dx, dx_ref)
+    tot = stats.double().sum(0)[:, :cs]
+    m = (zprev.double() * scale.double() + shift.double()) > 0
+    gm = dx_ref.double() * m
+    ref1 = gm.reshape(-1, cs).sum(0)
+    ref2 = (gm * (zprev.double() - mean.double()) * invstd.double()).reshape(-1, cs).sum(0)
+    l1 = gm.abs().reshape(-1, cs).sum(0) + 1e-30
+    l2 = (gm * (zprev.double() - mean.double()) * invstd.double()).abs().reshape(-1, cs).sum(0) + 1e-30
+    assert float(((tot[0] - ref1).abs() / l1).max()) < 1e-5
+    assert float(((tot[1] - ref2).abs() / l2).max()) < 1e-5
+    # activation planes from the BatchNorm-backward apply pass == split_bf16 of relu(z*scale+shift)
+    sums = torch.zeros(2 * cs, dtype=torch.float64, device=cuda_device)
+    M = zprev.numel() // cs
+    d_hi, d_lo, a_hi, a_lo = (torch.empty(zprev.shape, dtype=torch.bfloat16, device=cuda_device) for _ in range(4))
+    _lib.check(_lib.lib().selavi_bn_bwd_apply(_lib.ptr(dx), _lib.ptr(zprev), None, 2, _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(mean),
+                                              _lib.ptr(invstd), _lib.ptr(sums), float(M), M, cs, None, None, 0, _lib.ptr(d_hi),
+                                              _lib.ptr(d_lo), _lib.ptr(a_hi), _lib.ptr(a_lo), _lib.stream_ptr()), "bn_bwd_apply")
+    e_hi, e_lo = ops.split_bf16(zprev, scale=scale, shift=shift, relu=True)
+    assert torch.equal(a_hi, e_hi) and torch.equal(a_lo, e_lo)
+
+
+@pytest.mark.parametrize("name", sorted(HALO_LAYERS))
 def test_conv_halo_cta_pair_matches_single_cta(cuda_device, name, monkeypatch):
     """CTA-pair variant (cluster of 2, tcgen05 cta_group::2, each CTA stages half of every weight tile): the MMAs see
     the same operands in the same order, so forward (with prologue + stats) and data gradient are bit-identical to the

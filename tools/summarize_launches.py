@@ -1,12 +1,26 @@
 """Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel name.
-usage: python tools/summarize_launches.py launches.csv [first_id last_id] > profiles/rXX_launch_list_summary.txt"""
+usage: python tools/summarize_launches.py launches.csv [first_id last_id | --step K] > profiles/rXX_launch_list_summary.txt"""
 import csv
 import re
 import sys
 
 
+def step_range(path, step):
+    """ID range of train step `step` (0-based): every step starts with the two nchw_to_cl launches (audio, video input)"""
+    ids = []
+    with open(path, newline="") as f:
+        lines = [l for l in f if not l.startswith("==")]
+    for r in csv.DictReader(lines):
+        if r.get("Metric Name") == "gpu__time_duration.sum" and "nchw_to_cl" in r["Kernel Name"]:
+            ids.append(int(r["ID"]))
+    return ids[2 * step], ids[2 * step + 2] - 1
+
+
 def main():
     path = sys.argv[1]
+    if len(sys.argv) > 3 and sys.argv[2] == "--step":
+        lo, hi = step_range(path, int(sys.argv[3]))
+        sys.argv = sys.argv[:2] + [str(lo), str(hi)]
     lo = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     hi = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 60
     rows = []
