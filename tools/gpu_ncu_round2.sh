@@ -11,10 +11,12 @@ timeout 900 ncu --set full --clock-control none -k regex:'wgrad_bf16_kernel|wgra
 echo "ncu wgrad rc=$?"
 python tools/ncu_traffic.py gpurun_out/ncu_wgrad_step_${TAG}.csv > gpurun_out/ncu_traffic_wgrad_${TAG}.json
 python tools/ncu_summary.py < gpurun_out/ncu_wgrad_step_${TAG}.csv > gpurun_out/ncu_wgrad_step_summary_${TAG}.txt
+if [ "$2" == "halo" ]; then
 # tap-reuse conv launches of step 3: 57 per step (28 forward + 29 data gradient)
 timeout 900 ncu --set full --clock-control none -k regex:conv_halo_kernel -s 171 -c 57 \
     --csv --page raw --log-file gpurun_out/ncu_halo_step_${TAG}.csv $BENCH > gpurun_out/ncu_halo_step_${TAG}.log 2>&1
 echo "ncu halo rc=$?"
 python tools/ncu_summary.py < gpurun_out/ncu_halo_step_${TAG}.csv > gpurun_out/ncu_halo_step_summary_${TAG}.txt
+fi
 cat gpurun_out/ncu_traffic_wgrad_${TAG}.json
-grep -c "^## launch" gpurun_out/ncu_wgrad_step_summary_${TAG}.txt gpurun_out/ncu_halo_step_summary_${TAG}.txt
+grep -c "^## launch" gpurun_out/ncu_wgrad_step_summary_${TAG}.txt
