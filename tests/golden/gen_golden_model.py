@@ -25,7 +25,7 @@ CONFIGS = {
     "cfg4_heads": (16, 8, 112, 99, 28, 10),
 }
 # configs replayed by the CPU-only oracle test (the batch-16 ones take too long for the "not gpu" suite)
-CPU_ORACLE_CONFIGS = ("cfg1",)
+CPU_ORACLE_CONFIGS = ("cfg1", "cfg4_heads")
 SMALL = ("bn", "bias", "mlp_v.block_forward.8", "mlp_a.block_forward.8", "mlp_v0.block_forward.8", "stem.0.weight",
          "audio_network.base.conv1.weight", "downsample.0.weight")
 
