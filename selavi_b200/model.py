@@ -305,6 +305,14 @@ class AVModel(nn.Module):
         for prefix, net, kind in towers:
             names += [f"{prefix}.{n}" for n, _ in net.named_parameters()]
             tensors += [p.data for _, p in net.named_parameters()]
+        # The side effects (switching the towers to engine-side gradient averaging, the state broadcast) happen only when
+        # DistributedDataParallel's constructor is the reader: any other introspection (inspect.getmembers, dir loops)
+        # just gets the names and cannot start a collective on one rank alone.
+        import sys
+        caller = sys._getframe(1)
+        if caller.f_globals.get("__name__") != "torch.nn.parallel.distributed":
+            return names
+        for prefix, net, kind in towers:
             runner = net.__dict__.get("_sv_runner")
             if runner is None:
                 runner = net.__dict__["_sv_runner"] = engine.TowerRunner(net, kind)

@@ -314,7 +314,13 @@ def _ddp_ignore_worker(rank, world, port, out):
     # what DistributedDataParallel.__init__ does with the attribute (torch/nn/parallel/distributed.py:723-736); DDP itself
     # refuses SyncBatchNorm modules on the CPU, the real construction is exercised by tests/test_multigpu.py
     assert hasattr(m, "_ddp_params_and_buffers_to_ignore")
-    ignore = set(m._ddp_params_and_buffers_to_ignore)
+    # any reader other than DDP's constructor gets the names without side effects (no collective, towers untouched)
+    assert m._ddp_params_and_buffers_to_ignore and "_sv_runner" not in m.video_network.base.__dict__
+    # the same access made from a frame of module torch.nn.parallel.distributed, as DistributedDataParallel.__init__ makes it
+    import types
+    code = compile("def read(module):\n    return module._ddp_params_and_buffers_to_ignore\n", "<ddp>", "exec")
+    read = types.FunctionType(code.co_consts[0], {"__name__": "torch.nn.parallel.distributed"})
+    ignore = set(read(m))
     reduced_by_ddp = [n for n, _ in m.named_parameters() if n not in ignore]
     # the ignored tensors were synchronised to rank 0's values here (DDP's own construction-time broadcast skips them)
     probe = torch.cat([m.video_network.base.stem[0].weight.detach().reshape(-1)[:64],
