@@ -12,8 +12,10 @@
 // over CTAs (split-K); partial tiles go to a [slices][taps*cs][co] buffer that wgrad_reduce sums in a fixed
 // order and scatters into the torch weight layout (deterministic, no atomics).
 #include <cuda_bf16.h>
+#include <cudaTypedefs.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "../../include/selavi_b200.h"
 #include "common.cuh"
@@ -379,6 +381,7 @@ struct WgradBf16Params {
     int G, groups;   // G consecutive 128-row tiles per CTA share every dz stage (one accumulator each)
     int stages, total_kstages;
     int passes;
+    int use_tma;     // 1: the column operand (dz planes) is fetched with cp.async.bulk.tensor (tensor maps tm_hi / tm_lo)
     uint32_t tmem_cols;
     WgSplit split;
 };
@@ -399,7 +402,13 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-__global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf16Params p) {
+// The column operand B (dz planes [M pixels][cd channels], MN-major) needs no per-element work: each 64-channel chunk of a
+// 32-pixel stage (4 SWIZZLE_128B atoms) is one TMA tiled box {64, 32} of a 2-D tensor map, written with the hardware's 128-byte swizzle
+// (identical to the (chunk ^ pixel & 7) pattern the cp.async path builds by hand), zero-filled beyond the last pixel /
+// channel, completing on the stage's mbarrier.  One thread issues them; the 256 loader threads keep the row operand
+// (tap-shifted gathers with per-pixel bounds, which a tiled box cannot express for the strided / padded cases).
+__global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf16Params p, const __grid_constant__ CUtensorMap tm_hi,
+                                                                   const __grid_constant__ CUtensorMap tm_lo) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int nchb = (p.bnt + 63) >> 6;              // 64-channel chunks of the B tile
@@ -420,11 +429,15 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf
 
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            sv::mbar_init(&full_bar[s], WB_LOADER_WARPS);
+            sv::mbar_init(&full_bar[s], WB_LOADER_WARPS + (p.use_tma ? 1 : 0));   // + the TMA issuer's arrive.expect_tx
             sv::mbar_init(&empty_bar[s], 1);
         }
         sv::mbar_init(accum_bar, 1);
         sv::fence_barrier_init();
+        if (p.use_tma) {
+            sv::tma_prefetch_desc(&tm_hi);
+            sv::tma_prefetch_desc(&tm_lo);
+        }
     }
     if (warp == WB_MMA_WARP) {
         sv::tmem_alloc(tmem_slot, p.tmem_cols);
@@ -476,7 +489,9 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf
             const int c0 = n_off + g8 * 8;
             const bool ok = px < WG_PIX && c0 < p.cd;
             b_px[j] = ok ? px : -1;
-            b_soff[j] = (uint32_t)(((px >> 3) * nchb + (g8 >> 3)) * 1024 + (px & 7) * 128 + (((g8 & 7) ^ (px & 7)) << 4));
+            // B tile layout [64-channel chunk][k-group of 8 pixels][8 rows x 128 B]: the 4 k-groups of a chunk are contiguous, so
+            // that ONE TMA box of 64 channels x 32 pixels fills a chunk (descriptor: LBO = 4 KB between chunks, SBO = 1 KB)
+            b_soff[j] = (uint32_t)(((g8 >> 3) * 4 + (px >> 3)) * 1024 + (px & 7) * 128 + (((g8 & 7) ^ (px & 7)) << 4));
             b_goff[j] = (long long)px * p.cd + c0;
         }
         int stage = 0;
@@ -517,10 +532,23 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf
                     }
                 }
             }
+            if (p.use_tma) {
+                if (tid == 0) {   // nchb channel chunks x (hi, lo): one 64-channel x 32-pixel box (4 SWIZZLE_128B atoms) each
+                    sv::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(with_lo ? 2 * b_bytes : b_bytes));
+                    for (int c = 0; c < nchb; ++c) {
+                        const uint32_t off = (uint32_t)(c * 4096);
+                        sv::tma_load_2d(smem + (size_t)stage * stage_bytes + (size_t)(p.G * 2 * WB_A_BYTES) + off, &tm_hi,
+                                        &full_bar[stage], n_off + c * 64, ks * WG_PIX);
+                        if (with_lo)
+                            sv::tma_load_2d(smem + (size_t)stage * stage_bytes + (size_t)(p.G * 2 * WB_A_BYTES) + b_bytes + off,
+                                            &tm_lo, &full_bar[stage], n_off + c * 64, ks * WG_PIX);
+                    }
+                }
+            }
             const long long zbase = (long long)ks * WG_PIX * p.cd;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (b_px[j] >= 0) {
+                if (!p.use_tma && b_px[j] >= 0) {
                     const bool ok = ks * WG_PIX + b_px[j] < p.M;
                     const size_t off = ok ? (size_t)(zbase + b_goff[j]) : 0;
                     const uint32_t nbytes = ok ? 16u : 0u;
@@ -577,8 +605,8 @@ __global__ void __launch_bounds__(WB_THREADS, 1) wgrad_bf16_kernel(const WgradBf
             const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t a_sbo = 2 * 1024, b_sbo = (uint32_t)(nchb * 1024);
-            const uint64_t a_fixed = sv::make_smem_desc(0, 1024, a_sbo, 2), b_fixed = sv::make_smem_desc(0, 1024, b_sbo, 2);
+            const uint32_t a_sbo = 2 * 1024, b_sbo = 1024;   // byte stride between k-groups of 8 pixels (A: [k-group][chunk], B: [chunk][k-group])
+            const uint64_t a_fixed = sv::make_smem_desc(0, 1024, a_sbo, 2), b_fixed = sv::make_smem_desc(0, 4096, b_sbo, 2);
             for (int i = 0; i < nks; ++i) {
                 sv::mbar_wait(&full_bar[stage], phase);
                 sv::tc_fence_after();
@@ -795,6 +823,30 @@ extern "C" size_t selavi_wgrad_workspace_bytes(const int* geom) {
 
 namespace {
 
+// 2-D tensor map over a bf16 plane [rows][cols] (cols contiguous): box = 64 columns x 32 rows (the pixels of one stage)
+bool make_plane_map(CUtensorMap* tm, const void* base, long long rows, int cols) {
+    static PFN_cuTensorMapEncodeTiled encode = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+        else
+            cudaGetLastError();
+    }
+    if (!encode || (reinterpret_cast<uintptr_t>(base) & 15) || (cols & 7)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    const cuuint32_t box[2] = {64, 32};     // one 64-channel chunk of a pixel stage = 4 consecutive SWIZZLE_128B atoms
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int blocks_for(long long n) {
     long long b = (n + 255) / 256;
     return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
@@ -886,9 +938,16 @@ int wgrad_run(const float* src, const float* dz, const void* z_hi_in, const void
         q.G = pl.G; q.groups = pl.groups;
         q.stages = p.stages; q.total_kstages = p.total_kstages; q.split = pl.split;
         q.passes = p.passes; q.tmem_cols = p.tmem_cols;
+        // column operand through the TMA engine (SELAVI_WGRAD_TMA=0: the cp.async loaders fetch it as in round 1); its rows
+        // are the OUTPUT pixels (or, with exchanged operands on a stride-1 "same" conv, the equally many input pixels)
+        alignas(64) CUtensorMap tm_hi, tm_lo;
+        memset(&tm_hi, 0, sizeof(tm_hi));
+        memset(&tm_lo, 0, sizeof(tm_lo));
+        static const bool want_tma = !(getenv("SELAVI_WGRAD_TMA") && atoi(getenv("SELAVI_WGRAD_TMA")) == 0);
+        q.use_tma = (want_tma && make_plane_map(&tm_hi, q.z_hi, M, q.cd) && make_plane_map(&tm_lo, q.z_lo, M, q.cd)) ? 1 : 0;
         SV_CUDA_CHECK(cudaFuncSetAttribute(wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                       "conv_wgrad: cudaFuncSetAttribute");
-        wgrad_bf16_kernel<<<grid, WB_THREADS, smem, stream>>>(q);
+        wgrad_bf16_kernel<<<grid, WB_THREADS, smem, stream>>>(q, tm_hi, tm_lo);
     } else {
         SV_CUDA_CHECK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                       "conv_wgrad: cudaFuncSetAttribute");
