@@ -15,7 +15,7 @@ KEEP = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
 
 def main():
     labels = sys.argv[1:]
-    rows = list(csv.reader(l for l in sys.stdin if not l.startswith("==")))
+    rows = list(csv.reader(l for l in sys.stdin if l.strip() and not l.startswith("==")))
     if len(rows) < 3:
         print("no data")
         return

@@ -23,7 +23,7 @@ def main():
     lo = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     hi = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 60
     with open(path, newline="") as f:
-        lines = [l for l in f if not l.startswith("==")]
+        lines = [l for l in f if l.strip() and not l.startswith("==")]
     rows = list(csv.reader(lines))
     hdr = rows[0]
     ci = {n: i for i, n in enumerate(hdr)}
