@@ -247,7 +247,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))   # a hang fails fast
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=480))   # a hang fails in minutes, not tens of minutes
         dist.barrier()
     _lib.lib()
     pk = peaks()
@@ -276,6 +276,8 @@ def run_ours(args):
     # nearly identical, and the heads' BatchNorm1d over such a batch amplifies ANY rounding difference ~100x (for logits on
     # a well-conditioned batch see profiles/r02_precision_modes.txt: 1.4e-2 fast vs 6.0e-5 parity at this shape).
     fast_err = None
+    if world > 1:
+        args.no_fast_mode = True      # a single-GPU numerics reference point; not repeated under data parallelism
     if not args.no_fast_mode:
         try:
             model.return_features = True

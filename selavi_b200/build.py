@@ -57,7 +57,7 @@ def build(force=False, verbose=False):
         print("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed, see selavi_b200/lib/build.log")
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-Xcompiler", "-fPIC"]
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart", "-Xcompiler", "-fPIC"]
     subprocess.check_call(cmd)
     open(stamp, "w").write(dig)
     return LIB
