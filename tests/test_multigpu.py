@@ -47,9 +47,10 @@ def oracle_file(tmp_path_factory):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_multi_gpu_parity(cuda_device, oracle_file, world):
+def test_multi_gpu_parity(cuda_device, request, world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} visible GPUs, found {torch.cuda.device_count()}")
+    oracle_file = request.getfixturevalue("oracle_file")      # (the float64 CPU oracle is only computed when a case runs)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29530 + world), os.path.join(ROOT, "tests", "mgpu_worker.py"), oracle_file]
     res = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=420)
