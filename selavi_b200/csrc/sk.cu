@@ -261,17 +261,24 @@ __global__ void __launch_bounds__(SK_THREADS, 1) sk_kernel(const SkArgs a) {
                 for (int rr = first; rr < nr; rr += SK_WARPS) {
                     const long long n = r0 + rr;
                     double x[KPL];
+                    const double* rowp = rows + rr * K;
+                    // (ncu: the kernel issues 278 instructions per row and half of all issue slots are busy — the odd-tail
+                    // test used to sit inside the element loop as a branch around a global load; it concerns one row of
+                    // one chunk of the last CTA)
+                    if (!(tail8 && rr == nr - 1)) {
 #pragma unroll
-                    for (int i = 0; i < KPL; ++i) {
-                        const int k = lane + 32 * i;
-                        double v = 0.0;
-                        if (k < K) {
-                            if (tail8 && rr == nr - 1 && k == K - 1)
-                                v = a.PS[(size_t)n * K + k];
-                            else
-                                v = rows[(size_t)rr * K + k];
+                        for (int i = 0; i < KPL; ++i) {
+                            const int k = lane + 32 * i;
+                            x[i] = (k < K) ? rowp[k] : 0.0;
                         }
-                        x[i] = v;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < KPL; ++i) {
+                            const int k = lane + 32 * i;
+                            double v = 0.0;
+                            if (k < K) v = (k == K - 1) ? a.PS[(size_t)n * K + k] : rowp[k];
+                            x[i] = v;
+                        }
                     }
                     if (mode == MODE_PREP) {
 #pragma unroll
