@@ -46,11 +46,19 @@ def load_utils_get_loss():
     return mod.get_loss
 
 
-def load_sk_module(device="cpu"):
-    """reference src/sk_utils.py with its hard-coded cuda device strings substituted (text-level)."""
+def load_sk_module(device="cpu", sweep=False):
+    """reference src/sk_utils.py with its hard-coded cuda device strings substituted (text-level).
+    sweep=True additionally neutralises the CUDA-only spellings of `get_cluster_assignments_gpu` / `match_order`
+    (non-blocking copies, torch.cuda tensor types, synchronize / empty_cache, `.to('cuda')`) so that the whole sweep +
+    assignment bookkeeping runs on the CPU under a single-process gloo group; no arithmetic or control flow changes."""
     src = open(os.path.join(REF, "src", "sk_utils.py")).read()
     if device == "cpu":
         src = src.replace("device='cuda:0'", "device='cpu'").replace("device='cuda'", "device='cpu'")
+        if sweep:
+            src = src.replace(".cuda(non_blocking=True)", "")
+            src = src.replace("torch.cuda.DoubleTensor", "torch.DoubleTensor").replace("torch.cuda.FloatTensor", "torch.FloatTensor")
+            src = src.replace("torch.cuda.synchronize()", "None").replace("torch.cuda.empty_cache()", "None")
+            src = src.replace(".to('cuda')", "")
         src = src.replace(".cuda()", "")
     mod = types.ModuleType("ref_sk_utils")
     mod.__file__ = os.path.join(REF, "src", "sk_utils.py")

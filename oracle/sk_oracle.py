@@ -4,7 +4,9 @@ Restates /root/reference/src/sk_utils.py:359-422 (`optimize_L_sk_gpu`) line by l
 the Gaussian marginals (sk_utils.py:372,377) is an INPUT here (`kdist`) so that the oracle, the reference
 and the CUDA kernel can share it.  Pinned against the reference itself (device strings substituted, see
 oracle/ref_loader.py) by tests/golden/gen_golden.py -> tests/golden/sk_*.npz, checked in
-tests/test_oracle.py.
+tests/test_oracle.py.  `cluster_assignments_oracle` / `match_order_oracle` (the sweep bookkeeping and the head
+alignment, src/sk_utils.py:137-467) are pinned by tests/test_reference_bookkeeping.py, which runs the unmodified
+reference functions on the CPU next to them.
 """
 import numpy as np
 
