@@ -112,3 +112,43 @@ def test_bookkeeping_oracle_matches_reference(gloo_group, hc, K, match, ind_grou
         else:
             assert torch.equal(w, w0[h])
     assert m.training and m.return_features is False
+
+
+class _Rec:
+    def __init__(self):
+        self.lines = []
+
+    def info(self, msg, **_k):
+        self.lines.append(str(msg))
+
+
+def test_cluster_logging_matches_reference(gloo_group):
+    """`cluster()` (src/sk_utils.py:23-134): the NMI / adjusted-NMI / entropy / purity log lines of the mirror
+    (selavi_b200.sk_utils._log_label_metrics) equal the reference's for the same old and new labels (10th call: the
+    entropy / purity block is active)."""
+    from selavi_b200.sk_utils import _log_label_metrics
+    ref = ref_loader.load_sk_module("cpu", sweep=True)
+    hc, K, N = 2, 8, 96
+    ds = _Clips(N)
+    ds._labels = np.random.default_rng(3).integers(0, 5, N).tolist()
+    ds.valid_indices = np.arange(N)
+    torch.manual_seed(31)
+    m = OracleAVModel(hc, K)
+    m.use_mlp = True
+    m.train()
+    with torch.no_grad():
+        for it in range(10):
+            m(ds.v[it * 8:it * 8 + 16], ds.a[it * 8:it * 8 + 16])
+    args = types.SimpleNamespace(world_size=1, rank=0, workers=0, ind_groups=1, headcount=hc, match=False, distribution="default",
+                                 dist=None, diff_dist_every=False, diff_dist_per_head=True, gauss_sd=0.1, lamb=20, dump_path="")
+    old = torch.from_numpy(np.random.default_rng(4).integers(0, K, (N, hc)))
+    log_ref = _Rec()
+    np.random.seed(1)
+    torch.manual_seed(1)
+    new = ref.cluster(args, old.clone(), ds, _DDP(m), 9, log_ref, None, None, 3)
+    log_mine = _Rec()
+    _log_label_metrics(args, new, old, ds, 10, log_mine, None, 3)
+    keys = ("NMI_v:", "NMI-tolabels:", "aNMI-tolabels:", "Avg entropy:", "Avg purity:")
+    pick = lambda lines: [l for l in lines if l.startswith(keys)]      # noqa: E731
+    assert len(pick(log_ref.lines)) == 5
+    assert pick(log_mine.lines) == pick(log_ref.lines)
